@@ -1,0 +1,175 @@
+"""gemm_hls_b200 — B200-native MatrixMultiplication hot path of spcl/gemm_hls.
+
+Thin ctypes binding over the C-ABI library ``libmm_b200.so`` (include/mm_b200.h).  The product is
+the CUDA library; this module only loads it and passes pointers.  There is no CPU fallback: if the
+library is missing or no B200 is present the calls raise.
+
+Reference surface mirrored here (file:line under the reference checkout):
+  * ``MatrixMultiplicationKernel(a, b, c, n, k, m)``  include/MatrixMultiplication.h:155-171
+      -> :func:`matrix_multiplication_kernel` (host arrays in, host array out)
+  * ``hlslib::ocl::Context`` / ``MakeBuffer`` / ``CopyFromHost`` / ``MakeKernel`` / ``ExecuteTask``
+      host/RunHardware.cpp:116-190  -> :class:`Context`
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmm_b200.so")
+
+# MM_DATA_TYPE codes
+HALF, FLOAT, DOUBLE, INT32, UINT32, UINT8 = range(6)
+# MM_MAP_OP / MM_REDUCE_OP codes (hlslib::op functors)
+MULTIPLY, ADD, MIN, MAX, AND = range(5)
+# flags
+FLAG_NONE, FLAG_TRANSPOSED_A, FLAG_EXACT, FLAG_TF32X3 = 0, 1, 2, 4
+
+NP_DTYPE = {HALF: np.float16, FLOAT: np.float32, DOUBLE: np.float64,
+            INT32: np.int32, UINT32: np.uint32, UINT8: np.uint8}
+DTYPE_FROM_NAME = {"half": HALF, "float": FLOAT, "double": DOUBLE, "int": INT32,
+                   "unsigned": UINT32, "unsigned int": UINT32, "uint8_t": UINT8}
+OP_FROM_NAME = {"Multiply": MULTIPLY, "Product": MULTIPLY, "Add": ADD, "Sum": ADD,
+                "Min": MIN, "Max": MAX, "And": AND}
+
+EXPORTS = ["mm_last_error", "mm_version", "mm_dtype_size", "mm_memory_width", "mm_context_create",
+           "mm_context_destroy", "mm_buffer_alloc", "mm_buffer_free", "mm_copy_to_device",
+           "mm_copy_to_host", "mm_kernel_execute", "mm_kernel_enqueue", "mm_kernel_launch_count",
+           "mm_kernel_path", "mm_gemm_host"]
+
+
+class MMError(RuntimeError):
+    """Counterpart of hlslib::ocl::RuntimeError / ConfigurationError (common/OpenCL.h:99-157)."""
+
+    def __init__(self, code, message):
+        super().__init__("mm_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libmm_b200.so; raises if it has not been built (python gemm_hls_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MMError(-1, "%s not found — build it with `python gemm_hls_b200/build.py` "
+                              "(there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i, u, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.mm_last_error.restype = ctypes.c_char_p
+        L.mm_dtype_size.argtypes, L.mm_dtype_size.restype = [i], sz
+        L.mm_memory_width.argtypes, L.mm_memory_width.restype = [i], u
+        L.mm_context_create.argtypes = [i, ctypes.POINTER(vp)]
+        L.mm_context_destroy.argtypes = [vp]
+        L.mm_buffer_alloc.argtypes = [vp, sz, ctypes.POINTER(vp)]
+        L.mm_buffer_free.argtypes = [vp, vp]
+        L.mm_copy_to_device.argtypes = [vp, vp, vp, sz]
+        L.mm_copy_to_host.argtypes = [vp, vp, vp, sz]
+        L.mm_kernel_execute.argtypes = [vp, i, i, i, i, vp, vp, vp, u, u, u, dp, dp]
+        L.mm_kernel_enqueue.argtypes = [vp, i, i, i, i, vp, vp, vp, u, u, u, vp]
+        L.mm_kernel_launch_count.argtypes = [i, i, i, i]
+        L.mm_kernel_path.argtypes, L.mm_kernel_path.restype = [i, i, i, i], ctypes.c_char_p
+        L.mm_gemm_host.argtypes = [vp, i, i, i, i, vp, vp, vp, u, u, u, dp, dp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise MMError(rc, lib().mm_last_error().decode())
+
+
+def memory_width(dtype):
+    return int(lib().mm_memory_width(dtype))
+
+
+def kernel_path(dtype, map_op=MULTIPLY, reduce_op=ADD, flags=0):
+    return lib().mm_kernel_path(dtype, map_op, reduce_op, flags).decode()
+
+
+def launch_count(dtype, map_op=MULTIPLY, reduce_op=ADD, flags=0):
+    return int(lib().mm_kernel_launch_count(dtype, map_op, reduce_op, flags))
+
+
+class Context:
+    """Device context: the hlslib::ocl::Context + Program + Kernel of host/RunHardware.cpp:116-162."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        _check(lib().mm_context_create(device, ctypes.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().mm_context_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # Context::MakeBuffer
+    def alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        _check(lib().mm_buffer_alloc(self._h, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def free(self, dptr):
+        _check(lib().mm_buffer_free(self._h, dptr))
+
+    # Buffer::CopyFromHost / CopyToHost
+    def copy_to_device(self, dptr, host_array):
+        host_array = np.ascontiguousarray(host_array)
+        _check(lib().mm_copy_to_device(self._h, dptr, host_array.ctypes.data, host_array.nbytes))
+
+    def copy_to_host(self, host_array, dptr):
+        assert host_array.flags["C_CONTIGUOUS"]
+        _check(lib().mm_copy_to_host(self._h, host_array.ctypes.data, dptr, host_array.nbytes))
+
+    # Kernel::ExecuteTask -> (seconds_device, seconds_wall)
+    def execute(self, dtype, map_op, reduce_op, a_dev, b_dev, c_dev, n, k, m, flags=0):
+        sd, sw = ctypes.c_double(), ctypes.c_double()
+        _check(lib().mm_kernel_execute(self._h, dtype, map_op, reduce_op, flags, a_dev, b_dev, c_dev,
+                                       n, k, m, ctypes.byref(sd), ctypes.byref(sw)))
+        return sd.value, sw.value
+
+    def enqueue(self, dtype, map_op, reduce_op, a_dev, b_dev, c_dev, n, k, m, flags=0, stream=None):
+        """Asynchronous launch on a CUDA stream handle (int, e.g. torch's stream.cuda_stream)."""
+        _check(lib().mm_kernel_enqueue(self._h, dtype, map_op, reduce_op, flags, a_dev, b_dev, c_dev,
+                                       n, k, m, ctypes.c_void_p(stream) if stream else None))
+
+    def gemm_host(self, dtype, map_op, reduce_op, a, b, n, k, m, flags=0, out=None):
+        """Host arrays in, host array out (H2D, kernel, D2H); returns (C, seconds_device, seconds_wall)."""
+        return _gemm_host(self._h, dtype, map_op, reduce_op, a, b, n, k, m, flags, out)
+
+
+def _gemm_host(handle, dtype, map_op, reduce_op, a, b, n, k, m, flags, out):
+    npdt = NP_DTYPE.get(dtype)  # unknown codes are rejected by the library itself (MM_ERR_INVALID)
+    a = np.ascontiguousarray(a, dtype=npdt).reshape(-1)
+    b = np.ascontiguousarray(b, dtype=npdt).reshape(-1)
+    if npdt is not None and (a.size != n * k or b.size != k * m):
+        raise MMError(1, "A must hold n*k and B k*m elements")
+    c = out if out is not None else np.empty((n, m), dtype=npdt if npdt is not None else a.dtype)
+    sd, sw = ctypes.c_double(), ctypes.c_double()
+    _check(lib().mm_gemm_host(handle, dtype, map_op, reduce_op, flags, a.ctypes.data, b.ctypes.data,
+                              c.ctypes.data, n, k, m, ctypes.byref(sd), ctypes.byref(sw)))
+    return c, sd.value, sw.value
+
+
+def matrix_multiplication_kernel(a, b, n, k, m, dtype=FLOAT, map_op=MULTIPLY, reduce_op=ADD, flags=0):
+    """The reference's ``MatrixMultiplicationKernel(a, b, c, n, k, m)`` called with host pointers
+    (test/TestSimulation.cpp:66), for a run-time chosen (MM_DATA_TYPE, MM_MAP_OP, MM_REDUCE_OP).
+    Returns C as an (n, m) numpy array.  Uses the library's default context on device 0."""
+    c, _, _ = _gemm_host(None, dtype, map_op, reduce_op, a, b, n, k, m, flags, None)
+    return c

@@ -1,0 +1,309 @@
+// C-ABI of libmm_b200.so (include/mm_b200.h): context / buffer lifecycle mirroring the
+// hlslib::ocl calls of host/RunHardware.cpp:116-190, and the dispatch of one
+// MatrixMultiplicationKernel invocation onto the B200 kernel families.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+namespace mm {
+
+namespace {
+thread_local std::string g_last_error = "";
+}
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+int fail(int code, const std::string &msg) {
+  set_error(msg);
+  return code;
+}
+
+}  // namespace mm
+
+struct mm_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  mm::Scratch scratch;       // operand copies of the tensor-core path
+  mm::Scratch staging[3];    // device A, B, C of mm_gemm_host
+  std::mutex mutex;          // entry points are blocking and serialised per context, like
+                             // hlslib::ocl::Context's enqueue/memcopy mutexes (common/OpenCL.h:474-492)
+};
+
+namespace {
+
+using mm::fail;
+
+bool valid_dtype(int d) { return d >= 0 && d < MM_DTYPE_COUNT; }
+bool valid_op(int o) { return o >= 0 && o < MM_OP_COUNT; }
+
+enum Path { kPathTcgen05, kPathDmma, kPathSemiring };
+
+Path select_path(int dtype, int map_op, int reduce_op, int flags) {
+  const bool dense = (map_op == MM_OP_MULTIPLY && reduce_op == MM_OP_ADD) && !(flags & MM_FLAG_EXACT);
+  if (dense && (dtype == MM_DTYPE_FLOAT || dtype == MM_DTYPE_HALF)) return kPathTcgen05;
+  if (dense && dtype == MM_DTYPE_DOUBLE) return kPathDmma;
+  return kPathSemiring;
+}
+
+int ensure(mm::Scratch &s, size_t bytes) {
+  if (s.bytes >= bytes) return MM_OK;
+  if (s.ptr) cudaFree(s.ptr);
+  s.ptr = nullptr;
+  s.bytes = 0;
+  cudaError_t e = cudaMalloc(&s.ptr, bytes);
+  if (e != cudaSuccess) {
+    return fail(e == cudaErrorMemoryAllocation ? MM_ERR_NOMEM : MM_ERR_CUDA,
+                std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  }
+  s.bytes = bytes;
+  return MM_OK;
+}
+
+int check_args(int dtype, int map_op, int reduce_op, const void *a, const void *b, const void *c,
+               unsigned n, unsigned k, unsigned m) {
+  if (!valid_dtype(dtype)) return fail(MM_ERR_INVALID, "unknown MM_DATA_TYPE code");
+  if (!valid_op(map_op) || !valid_op(reduce_op)) return fail(MM_ERR_INVALID, "unknown MM_MAP_OP / MM_REDUCE_OP code");
+  if (!a || !b || !c) return fail(MM_ERR_INVALID, "null matrix pointer");
+  if (n == 0 || k == 0 || m == 0) return fail(MM_ERR_INVALID, "matrix dimensions must be positive");
+  const unsigned w = mm_memory_width(dtype);
+  // same rule and wording as host/RunHardware.cpp:50-61
+  if (k % w != 0) {
+    return fail(MM_ERR_SHAPE, "K (" + std::to_string(k) + ") must be divisable by the memory width in K (" +
+                                  std::to_string(w) + ").");
+  }
+  if (m % w != 0) {
+    return fail(MM_ERR_SHAPE, "M (" + std::to_string(m) + ") must be divisable by the memory width in M (" +
+                                  std::to_string(w) + ").");
+  }
+  return MM_OK;
+}
+
+int enqueue_locked(mm_context *ctx, int dtype, int map_op, int reduce_op, int flags, const void *a,
+                   const void *b, void *c, unsigned n, unsigned k, unsigned m, cudaStream_t stream) {
+  mm::GemmArgs g{a, b, c, n, k, m, flags, stream};
+  Path path = select_path(dtype, map_op, reduce_op, flags);
+  if (path == kPathDmma && (flags & MM_FLAG_TRANSPOSED_A) && (n % 2 != 0)) path = kPathSemiring;
+  switch (path) {
+    case kPathTcgen05: {
+      const size_t need = mm::tcgen05_scratch_bytes(dtype, n, k, m, flags);
+      int rc = ensure(ctx->scratch, need);
+      if (rc != MM_OK) return rc;
+      return mm::launch_tcgen05(dtype, g, ctx->scratch.ptr, ctx->scratch.bytes);
+    }
+    case kPathDmma:
+      return mm::launch_dmma(g);
+    case kPathSemiring:
+      return mm::launch_semiring(dtype, map_op, reduce_op, g);
+  }
+  return fail(MM_ERR_INVALID, "no kernel path");
+}
+
+std::mutex g_default_mutex;
+mm_context *g_default_ctx = nullptr;
+
+}  // namespace
+
+extern "C" {
+
+const char *mm_last_error(void) { return mm::g_last_error.c_str(); }
+
+int mm_version(void) { return 100; }
+
+size_t mm_dtype_size(int dtype) {
+  switch (dtype) {
+    case MM_DTYPE_HALF: return 2;
+    case MM_DTYPE_FLOAT: return 4;
+    case MM_DTYPE_DOUBLE: return 8;
+    case MM_DTYPE_INT32: return 4;
+    case MM_DTYPE_UINT32: return 4;
+    case MM_DTYPE_UINT8: return 1;
+  }
+  return 0;
+}
+
+unsigned mm_memory_width(int dtype) {
+  const size_t s = mm_dtype_size(dtype);
+  return s ? static_cast<unsigned>(64 / s) : 0;
+}
+
+int mm_context_create(int device, mm_context **out) {
+  if (!out) return fail(MM_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    return fail(MM_ERR_CUDA, std::string("no CUDA device available: ") +
+                                 (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  }
+  if (device < 0 || device >= count) return fail(MM_ERR_INVALID, "device ordinal out of range");
+  MM_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MM_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    return fail(MM_ERR_UNSUPPORTED, std::string("libmm_b200 is built for sm_100a only; device is sm_") +
+                                        std::to_string(prop.major) + std::to_string(prop.minor));
+  }
+  mm_context *ctx = new mm_context();
+  ctx->device = device;
+  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  MM_CUDA_TRY(cudaEventCreate(&ctx->ev_start));
+  MM_CUDA_TRY(cudaEventCreate(&ctx->ev_stop));
+  *out = ctx;
+  return MM_OK;
+}
+
+int mm_context_destroy(mm_context *ctx) {
+  if (!ctx) return MM_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
+  for (auto &s : ctx->staging) {
+    if (s.ptr) cudaFree(s.ptr);
+  }
+  cudaEventDestroy(ctx->ev_start);
+  cudaEventDestroy(ctx->ev_stop);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return MM_OK;
+}
+
+int mm_buffer_alloc(mm_context *ctx, size_t bytes, void **device_ptr) {
+  if (!ctx || !device_ptr) return fail(MM_ERR_INVALID, "null argument");
+  *device_ptr = nullptr;
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaError_t e = cudaMalloc(device_ptr, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    return fail(e == cudaErrorMemoryAllocation ? MM_ERR_NOMEM : MM_ERR_CUDA,
+                std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  return MM_OK;
+}
+
+int mm_buffer_free(mm_context *ctx, void *device_ptr) {
+  if (!ctx) return fail(MM_ERR_INVALID, "null context");
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
+  MM_CUDA_TRY(cudaFree(device_ptr));
+  return MM_OK;
+}
+
+int mm_copy_to_device(mm_context *ctx, void *device_dst, const void *host_src, size_t bytes) {
+  if (!ctx || !device_dst || !host_src) return fail(MM_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
+  MM_CUDA_TRY(cudaMemcpyAsync(device_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  MM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MM_OK;
+}
+
+int mm_copy_to_host(mm_context *ctx, void *host_dst, const void *device_src, size_t bytes) {
+  if (!ctx || !host_dst || !device_src) return fail(MM_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
+  MM_CUDA_TRY(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return MM_OK;
+}
+
+int mm_kernel_enqueue(mm_context *ctx, int dtype, int map_op, int reduce_op, int flags,
+                      const void *a, const void *b, void *c, unsigned n, unsigned k, unsigned m,
+                      void *cuda_stream) {
+  if (!ctx) return fail(MM_ERR_INVALID, "null context");
+  int rc = check_args(dtype, map_op, reduce_op, a, b, c, n, k, m);
+  if (rc != MM_OK) return rc;
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+  return enqueue_locked(ctx, dtype, map_op, reduce_op, flags, a, b, c, n, k, m, s);
+}
+
+int mm_kernel_execute(mm_context *ctx, int dtype, int map_op, int reduce_op, int flags,
+                      const void *a, const void *b, void *c, unsigned n, unsigned k, unsigned m,
+                      double *seconds_device, double *seconds_wall) {
+  if (!ctx) return fail(MM_ERR_INVALID, "null context");
+  int rc = check_args(dtype, map_op, reduce_op, a, b, c, n, k, m);
+  if (rc != MM_OK) return rc;
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
+  const auto t0 = std::chrono::high_resolution_clock::now();
+  MM_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
+  rc = enqueue_locked(ctx, dtype, map_op, reduce_op, flags, a, b, c, n, k, m, ctx->stream);
+  if (rc != MM_OK) return rc;
+  MM_CUDA_TRY(cudaEventRecord(ctx->ev_stop, ctx->stream));
+  MM_CUDA_TRY(cudaEventSynchronize(ctx->ev_stop));
+  const auto t1 = std::chrono::high_resolution_clock::now();
+  float ms = 0.f;
+  MM_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+  if (seconds_device) *seconds_device = 1e-3 * ms;
+  if (seconds_wall) *seconds_wall = std::chrono::duration<double>(t1 - t0).count();
+  return MM_OK;
+}
+
+int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags) {
+  if (!valid_dtype(dtype) || !valid_op(map_op) || !valid_op(reduce_op)) return -1;
+  switch (select_path(dtype, map_op, reduce_op, flags)) {
+    case kPathTcgen05:
+      // B^T prep + (A prep for float or transposed A) + GEMM
+      return (dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) ? 3 : 2;
+    case kPathDmma: return 1;
+    case kPathSemiring: return 1;
+  }
+  return -1;
+}
+
+const char *mm_kernel_path(int dtype, int map_op, int reduce_op, int flags) {
+  if (!valid_dtype(dtype) || !valid_op(map_op) || !valid_op(reduce_op)) return "invalid";
+  switch (select_path(dtype, map_op, reduce_op, flags)) {
+    case kPathTcgen05: return dtype == MM_DTYPE_FLOAT ? "tcgen05_tf32" : "tcgen05_f16";
+    case kPathDmma: return "dmma_f64";
+    case kPathSemiring: return "semiring_simt";
+  }
+  return "invalid";
+}
+
+int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flags, const void *a,
+                 const void *b, void *c, unsigned n, unsigned k, unsigned m, double *seconds_device,
+                 double *seconds_wall) {
+  int rc = check_args(dtype, map_op, reduce_op, a, b, c, n, k, m);
+  if (rc != MM_OK) return rc;
+  if (!ctx) {
+    std::lock_guard<std::mutex> lock(g_default_mutex);
+    if (!g_default_ctx) {
+      rc = mm_context_create(0, &g_default_ctx);
+      if (rc != MM_OK) return rc;
+    }
+    ctx = g_default_ctx;
+  }
+  const auto t0 = std::chrono::high_resolution_clock::now();
+  const size_t es = mm_dtype_size(dtype);
+  const size_t bytes_a = size_t(n) * k * es, bytes_b = size_t(k) * m * es, bytes_c = size_t(n) * m * es;
+  void *da, *db, *dc;
+  {
+    std::lock_guard<std::mutex> lock(ctx->mutex);
+    MM_CUDA_TRY(cudaSetDevice(ctx->device));
+    if ((rc = ensure(ctx->staging[0], bytes_a)) != MM_OK) return rc;
+    if ((rc = ensure(ctx->staging[1], bytes_b)) != MM_OK) return rc;
+    if ((rc = ensure(ctx->staging[2], bytes_c)) != MM_OK) return rc;
+    da = ctx->staging[0].ptr;
+    db = ctx->staging[1].ptr;
+    dc = ctx->staging[2].ptr;
+    MM_CUDA_TRY(cudaMemcpyAsync(da, a, bytes_a, cudaMemcpyHostToDevice, ctx->stream));
+    MM_CUDA_TRY(cudaMemcpyAsync(db, b, bytes_b, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  rc = mm_kernel_execute(ctx, dtype, map_op, reduce_op, flags, da, db, dc, n, k, m, seconds_device, nullptr);
+  if (rc != MM_OK) return rc;
+  {
+    std::lock_guard<std::mutex> lock(ctx->mutex);
+    MM_CUDA_TRY(cudaMemcpyAsync(c, dc, bytes_c, cudaMemcpyDeviceToHost, ctx->stream));
+    MM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  if (seconds_wall) {
+    *seconds_wall = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+  }
+  return MM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// Shared host-side helpers for the CUDA translation units of libmm_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/mm_b200.h"
+
+namespace mm {
+
+// Thread-local error message behind mm_last_error().
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define MM_CUDA_TRY(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t err__ = (expr);                                                            \
+    if (err__ != cudaSuccess) {                                                            \
+      return ::mm::fail(MM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    }                                                                                      \
+  } while (0)
+
+inline unsigned ceil_div(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+// Scratch the tensor-core path needs (rounded / transposed operand copies); owned by the
+// context, grown on demand, reused across calls.
+struct Scratch {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct GemmArgs {
+  const void *a;
+  const void *b;
+  void *c;
+  unsigned n, k, m;
+  int flags;
+  cudaStream_t stream;
+};
+
+// ---- kernel families (one launcher per translation unit) ---------------------------------------
+// CUDA-core semiring tile kernel, any (dtype, map, reduce).  semiring_*.cu
+int launch_semiring(int dtype, int map_op, int reduce_op, const GemmArgs &args);
+
+// tcgen05 tensor-core GEMM for (Multiply, Add) float (kind::tf32) and half (kind::f16).
+// `scratch_a` / `scratch_b` hold the K-major operand copies.  gemm_tcgen05.cu
+size_t tcgen05_scratch_bytes(int dtype, unsigned n, unsigned k, unsigned m, int flags);
+int launch_tcgen05(int dtype, const GemmArgs &args, void *scratch, size_t scratch_bytes);
+
+// DMMA (mma.sync m8n8k4 f64) GEMM for (Multiply, Add) double.  gemm_dmma.cu
+int launch_dmma(const GemmArgs &args);
+
+}  // namespace mm

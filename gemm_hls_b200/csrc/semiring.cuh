@@ -1,0 +1,151 @@
+// Semiring functors for the device kernels: same interface as the reference's hlslib::op
+// functors (hlslib/include/hlslib/xilinx/Operators.h:20-100) — `static T Apply(a, b)` and
+// `static constexpr T identity()` — so a (Map, Reduce) pair plugs into the kernels exactly like
+// MM_MAP_OP / MM_REDUCE_OP plug into the reference's ProcessingElement (kernel/Compute.cpp:129-133).
+//
+// Rounding contract: Apply() performs ONE correctly rounded operation in T (no FMA contraction
+// across Map and Reduce), so a kernel that reduces sequentially over k reproduces the
+// reference's Naive<> (include/Utility.h:18-42) bit for bit.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include <cfloat>
+#include <climits>
+#include <cstdint>
+
+#include "../../include/mm_b200.h"
+
+namespace mm {
+
+// ---- per-type primitives ---------------------------------------------------------------------
+template <typename T>
+struct Prim {
+  static __host__ __device__ __forceinline__ T add(T a, T b) { return static_cast<T>(a + b); }
+  static __host__ __device__ __forceinline__ T mul(T a, T b) { return static_cast<T>(a * b); }
+  static __host__ __device__ __forceinline__ bool lt(T a, T b) { return a < b; }
+  static __host__ __device__ __forceinline__ bool nz(T a) { return a != T(0); }
+  static __host__ __device__ __forceinline__ T zero() { return T(0); }
+  static __host__ __device__ __forceinline__ T one() { return T(1); }
+};
+
+template <>
+struct Prim<float> {
+  // __fadd_rn/__fmul_rn are never contracted into an FMA by the compiler.
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ bool lt(float a, float b) { return a < b; }
+  static __device__ __forceinline__ bool nz(float a) { return a != 0.0f; }
+  static __device__ __forceinline__ float zero() { return 0.0f; }
+  static __device__ __forceinline__ float one() { return 1.0f; }
+  // numeric_limits<float>::max() / ::min()
+  static __device__ __forceinline__ float max_value() { return FLT_MAX; }
+  static __device__ __forceinline__ float min_value() { return FLT_MIN; }
+};
+
+template <>
+struct Prim<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ bool lt(double a, double b) { return a < b; }
+  static __device__ __forceinline__ bool nz(double a) { return a != 0.0; }
+  static __device__ __forceinline__ double zero() { return 0.0; }
+  static __device__ __forceinline__ double one() { return 1.0; }
+  static __device__ __forceinline__ double max_value() { return DBL_MAX; }
+  static __device__ __forceinline__ double min_value() { return DBL_MIN; }
+};
+
+template <>
+struct Prim<__half> {
+  static __device__ __forceinline__ __half add(__half a, __half b) { return __hadd_rn(a, b); }
+  static __device__ __forceinline__ __half mul(__half a, __half b) { return __hmul_rn(a, b); }
+  static __device__ __forceinline__ bool lt(__half a, __half b) { return __hlt(a, b); }
+  static __device__ __forceinline__ bool nz(__half a) { return __hne(a, __ushort_as_half(0)); }
+  static __device__ __forceinline__ __half zero() { return __ushort_as_half(0x0000); }
+  static __device__ __forceinline__ __half one() { return __ushort_as_half(0x3C00); }
+  static __device__ __forceinline__ __half max_value() { return __ushort_as_half(0x7BFF); }  // 65504
+  static __device__ __forceinline__ __half min_value() { return __ushort_as_half(0x0400); }  // 2^-14
+};
+
+template <typename T>
+struct IntLimits;
+template <>
+struct IntLimits<int> {
+  static __host__ __device__ __forceinline__ int max_value() { return INT_MAX; }
+  static __host__ __device__ __forceinline__ int min_value() { return INT_MIN; }
+};
+template <>
+struct IntLimits<unsigned> {
+  static __host__ __device__ __forceinline__ unsigned max_value() { return UINT_MAX; }
+  static __host__ __device__ __forceinline__ unsigned min_value() { return 0u; }
+};
+template <>
+struct IntLimits<unsigned char> {
+  static __host__ __device__ __forceinline__ unsigned char max_value() { return 255; }
+  static __host__ __device__ __forceinline__ unsigned char min_value() { return 0; }
+};
+
+template <typename T>
+struct Lim {
+  static __device__ __forceinline__ T max_value() { return IntLimits<T>::max_value(); }
+  static __device__ __forceinline__ T min_value() { return IntLimits<T>::min_value(); }
+};
+template <> struct Lim<float> : Prim<float> {};
+template <> struct Lim<double> : Prim<double> {};
+template <> struct Lim<__half> : Prim<__half> {};
+
+// ---- the functors (Operators.h) ---------------------------------------------------------------
+template <typename T>
+struct Sum {  // Operators.h:20-33
+  static __device__ __forceinline__ T Apply(T a, T b) { return Prim<T>::add(a, b); }
+  static __device__ __forceinline__ T identity() { return Prim<T>::zero(); }
+};
+template <typename T>
+using Add = Sum<T>;  // Operators.h:35-36
+
+template <typename T>
+struct Product {  // Operators.h:45-58
+  static __device__ __forceinline__ T Apply(T a, T b) { return Prim<T>::mul(a, b); }
+  static __device__ __forceinline__ T identity() { return Prim<T>::one(); }
+};
+template <typename T>
+using Multiply = Product<T>;  // Operators.h:60-61
+
+template <typename T>
+struct And {  // Operators.h:63-74 — `a && b` converted back to T
+  static __device__ __forceinline__ T Apply(T a, T b) {
+    return (Prim<T>::nz(a) && Prim<T>::nz(b)) ? Prim<T>::one() : Prim<T>::zero();
+  }
+  static __device__ __forceinline__ T identity() { return Prim<T>::one(); }
+};
+
+template <typename T>
+struct Min {  // Operators.h:76-87
+  static __device__ __forceinline__ T Apply(T a, T b) { return Prim<T>::lt(a, b) ? a : b; }
+  static __device__ __forceinline__ T identity() { return Lim<T>::max_value(); }
+};
+
+template <typename T>
+struct Max {  // Operators.h:89-100 — identity is numeric_limits<T>::min() as in the reference
+  static __device__ __forceinline__ T Apply(T a, T b) { return Prim<T>::lt(b, a) ? a : b; }
+  static __device__ __forceinline__ T identity() { return Lim<T>::min_value(); }
+};
+
+template <typename T, int OP>
+struct OpSelect;
+template <typename T> struct OpSelect<T, MM_OP_MULTIPLY> { using type = Product<T>; };
+template <typename T> struct OpSelect<T, MM_OP_ADD> { using type = Sum<T>; };
+template <typename T> struct OpSelect<T, MM_OP_MIN> { using type = Min<T>; };
+template <typename T> struct OpSelect<T, MM_OP_MAX> { using type = Max<T>; };
+template <typename T> struct OpSelect<T, MM_OP_AND> { using type = And<T>; };
+
+// MM_DTYPE_* -> C type
+template <int DTYPE> struct DTypeOf;
+template <> struct DTypeOf<MM_DTYPE_HALF> { using type = __half; };
+template <> struct DTypeOf<MM_DTYPE_FLOAT> { using type = float; };
+template <> struct DTypeOf<MM_DTYPE_DOUBLE> { using type = double; };
+template <> struct DTypeOf<MM_DTYPE_INT32> { using type = int; };
+template <> struct DTypeOf<MM_DTYPE_UINT32> { using type = unsigned; };
+template <> struct DTypeOf<MM_DTYPE_UINT8> { using type = unsigned char; };
+
+}  // namespace mm
