@@ -35,7 +35,7 @@ OP_FROM_NAME = {"Multiply": MULTIPLY, "Product": MULTIPLY, "Add": ADD, "Sum": AD
 EXPORTS = ["mm_last_error", "mm_version", "mm_dtype_size", "mm_memory_width", "mm_context_create",
            "mm_context_destroy", "mm_buffer_alloc", "mm_buffer_free", "mm_copy_to_device",
            "mm_copy_to_host", "mm_kernel_execute", "mm_kernel_enqueue", "mm_kernel_launch_count",
-           "mm_kernel_path", "mm_gemm_host"]
+           "mm_kernel_path", "mm_gemm_host", "mm_context_set_profiling", "mm_context_profile_read"]
 
 
 class MMError(RuntimeError):
@@ -73,6 +73,8 @@ def lib():
         L.mm_kernel_launch_count.argtypes = [i, i, i, i]
         L.mm_kernel_path.argtypes, L.mm_kernel_path.restype = [i, i, i, i], ctypes.c_char_p
         L.mm_gemm_host.argtypes = [vp, i, i, i, i, vp, vp, vp, u, u, u, dp, dp]
+        L.mm_context_set_profiling.argtypes = [vp, i]
+        L.mm_context_profile_read.argtypes = [vp, dp, dp, ctypes.POINTER(i)]
         _lib = L
     return _lib
 
@@ -148,6 +150,15 @@ class Context:
         """Asynchronous launch on a CUDA stream handle (int, e.g. torch's stream.cuda_stream)."""
         _check(lib().mm_kernel_enqueue(self._h, dtype, map_op, reduce_op, flags, a_dev, b_dev, c_dev,
                                        n, k, m, ctypes.c_void_p(stream) if stream else None))
+
+    def set_profiling(self, enable=True):
+        _check(lib().mm_context_set_profiling(self._h, int(enable)))
+
+    def profile_read(self):
+        """(prep_seconds_sum, main_kernel_seconds_sum, calls) since the last read."""
+        p, mn, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        _check(lib().mm_context_profile_read(self._h, ctypes.byref(p), ctypes.byref(mn), ctypes.byref(c)))
+        return p.value, mn.value, c.value
 
     def gemm_host(self, dtype, map_op, reduce_op, a, b, n, k, m, flags=0, out=None):
         """Host arrays in, host array out (H2D, kernel, D2H); returns (C, seconds_device, seconds_wall)."""

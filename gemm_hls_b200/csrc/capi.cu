@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -29,6 +30,9 @@ struct mm_context {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   mm::Scratch scratch;       // operand copies of the tensor-core path
   mm::Scratch staging[3];    // device A, B, C of mm_gemm_host
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;  // 3 per profiled call: start, after prep, after main
+  int prof_calls = 0;
   std::mutex mutex;          // entry points are blocking and serialised per context, like
                              // hlslib::ocl::Context's enqueue/memcopy mutexes (common/OpenCL.h:474-492)
 };
@@ -85,6 +89,20 @@ int check_args(int dtype, int map_op, int reduce_op, const void *a, const void *
 int enqueue_locked(mm_context *ctx, int dtype, int map_op, int reduce_op, int flags, const void *a,
                    const void *b, void *c, unsigned n, unsigned k, unsigned m, cudaStream_t stream) {
   mm::GemmArgs g{a, b, c, n, k, m, flags, stream};
+  cudaEvent_t *pe = nullptr;
+  if (ctx->profiling && ctx->prof_calls < 256) {
+    while (ctx->prof_events.size() < size_t(3 * (ctx->prof_calls + 1))) {
+      cudaEvent_t e;
+      MM_CUDA_TRY(cudaEventCreate(&e));
+      ctx->prof_events.push_back(e);
+    }
+    pe = &ctx->prof_events[3 * ctx->prof_calls];
+    ++ctx->prof_calls;
+    g.ev_start = pe[0];
+    g.ev_prep_done = pe[1];
+    MM_CUDA_TRY(cudaEventRecord(pe[0], stream));
+  }
+  int rc_launch = MM_OK;
   Path path = select_path(dtype, map_op, reduce_op, flags);
   if (path == kPathDmma && (flags & MM_FLAG_TRANSPOSED_A) && (n % 2 != 0)) path = kPathSemiring;
   switch (path) {
@@ -92,14 +110,21 @@ int enqueue_locked(mm_context *ctx, int dtype, int map_op, int reduce_op, int fl
       const size_t need = mm::tcgen05_scratch_bytes(dtype, n, k, m, flags);
       int rc = ensure(ctx->scratch, need);
       if (rc != MM_OK) return rc;
-      return mm::launch_tcgen05(dtype, g, ctx->scratch.ptr, ctx->scratch.bytes);
+      rc_launch = mm::launch_tcgen05(dtype, g, ctx->scratch.ptr, ctx->scratch.bytes);
+      break;
     }
     case kPathDmma:
-      return mm::launch_dmma(g);
+      if (pe) MM_CUDA_TRY(cudaEventRecord(pe[1], stream));
+      rc_launch = mm::launch_dmma(g);
+      break;
     case kPathSemiring:
-      return mm::launch_semiring(dtype, map_op, reduce_op, g);
+      if (pe) MM_CUDA_TRY(cudaEventRecord(pe[1], stream));
+      rc_launch = mm::launch_semiring(dtype, map_op, reduce_op, g);
+      break;
   }
-  return fail(MM_ERR_INVALID, "no kernel path");
+  if (rc_launch != MM_OK) return rc_launch;
+  if (pe) MM_CUDA_TRY(cudaEventRecord(pe[2], stream));
+  return MM_OK;
 }
 
 std::mutex g_default_mutex;
@@ -164,6 +189,7 @@ int mm_context_destroy(mm_context *ctx) {
   for (auto &s : ctx->staging) {
     if (s.ptr) cudaFree(s.ptr);
   }
+  for (auto e : ctx->prof_events) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_start);
   cudaEventDestroy(ctx->ev_stop);
   cudaStreamDestroy(ctx->stream);
@@ -239,6 +265,35 @@ int mm_kernel_execute(mm_context *ctx, int dtype, int map_op, int reduce_op, int
   MM_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
   if (seconds_device) *seconds_device = 1e-3 * ms;
   if (seconds_wall) *seconds_wall = std::chrono::duration<double>(t1 - t0).count();
+  return MM_OK;
+}
+
+int mm_context_set_profiling(mm_context *ctx, int enable) {
+  if (!ctx) return fail(MM_ERR_INVALID, "null context");
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  ctx->profiling = enable != 0;
+  ctx->prof_calls = 0;
+  return MM_OK;
+}
+
+int mm_context_profile_read(mm_context *ctx, double *prep_sum, double *main_sum, int *calls) {
+  if (!ctx) return fail(MM_ERR_INVALID, "null context");
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
+  double prep = 0.0, main_s = 0.0;
+  for (int i = 0; i < ctx->prof_calls; ++i) {
+    cudaEvent_t *e = &ctx->prof_events[3 * i];
+    MM_CUDA_TRY(cudaEventSynchronize(e[2]));
+    float ms_prep = 0.f, ms_main = 0.f;
+    MM_CUDA_TRY(cudaEventElapsedTime(&ms_prep, e[0], e[1]));
+    MM_CUDA_TRY(cudaEventElapsedTime(&ms_main, e[1], e[2]));
+    prep += 1e-3 * ms_prep;
+    main_s += 1e-3 * ms_main;
+  }
+  if (prep_sum) *prep_sum = prep;
+  if (main_sum) *main_sum = main_s;
+  if (calls) *calls = ctx->prof_calls;
+  ctx->prof_calls = 0;
   return MM_OK;
 }
 

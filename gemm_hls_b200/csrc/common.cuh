@@ -38,6 +38,10 @@ struct GemmArgs {
   unsigned n, k, m;
   int flags;
   cudaStream_t stream;
+  // optional profiling events (capi.cu): recorded by the launcher between operand preparation
+  // and the main kernel when non-null
+  cudaEvent_t ev_start = nullptr;
+  cudaEvent_t ev_prep_done = nullptr;
 };
 
 // ---- kernel families (one launcher per translation unit) ---------------------------------------

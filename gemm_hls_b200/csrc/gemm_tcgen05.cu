@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -368,7 +369,16 @@ int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_b
 
   // ---- operand preparation ----
   const void *a_op = g.a;
-  if (is_f32) {
+  // Experiment hook (scripts/exp_tf32_rounding.py): feed raw fp32 bits to kind::tf32 to MEASURE the
+  // truncation bias that motivates the rounding pass.  Never set in production.
+  static const bool no_round = std::getenv("MM_EXPERIMENT_TF32_NO_ROUND") != nullptr;
+  if (is_f32 && no_round) {
+    launch_transpose<float, false>(g.b, bt, g.k, g.m, g.stream);
+    if (ta) {
+      launch_transpose<float, false>(g.a, aprep, g.k, g.n, g.stream);
+      a_op = aprep;
+    }
+  } else if (is_f32) {
     launch_transpose<float, true>(g.b, bt, g.k, g.m, g.stream);  // B (K x M) -> B^T (M x K), rounded
     if (ta) {
       launch_transpose<float, true>(g.a, aprep, g.k, g.n, g.stream);  // A stored K x N -> N x K
@@ -387,6 +397,7 @@ int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_b
     }
   }
   MM_CUDA_TRY(cudaGetLastError());
+  if (g.ev_prep_done) MM_CUDA_TRY(cudaEventRecord(g.ev_prep_done, g.stream));
 
   // ---- tensor maps + GEMM ----
   CUtensorMap map_a, map_b;

@@ -129,6 +129,15 @@ MM_API int mm_kernel_enqueue(mm_context *ctx, int dtype, int map_op, int reduce_
                       const void *a_device, const void *b_device, void *c_device, unsigned size_n,
                       unsigned size_k, unsigned size_m, void *cuda_stream);
 
+/* Per-phase device timing of enqueued work, for roofline accounting.  With profiling on, every
+ * mm_kernel_enqueue()/mm_kernel_execute() records CUDA events on the launching stream around
+ * (i) the operand-preparation kernels and (ii) the main compute kernel.  mm_context_profile_read()
+ * synchronises on the recorded events, returns the SUMS over the calls since the last read (at
+ * most 256 calls are kept) and the number of calls, and resets the counters. */
+MM_API int mm_context_set_profiling(mm_context *ctx, int enable);
+MM_API int mm_context_profile_read(mm_context *ctx, double *prep_seconds_sum,
+                                   double *main_seconds_sum, int *calls);
+
 /* Number of kernels one mm_kernel_enqueue() with these arguments launches (for accounting). */
 MM_API int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags);
 
