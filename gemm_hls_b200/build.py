@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 2))) as ex:
         jobs = [("semiring_inst.cu", "semiring_%s_%d.o" % (suffix, mp),
                  ["-DMM_INST_T=" + ctype, "-DMM_INST_MAP=%d" % mp])
-                for suffix, ctype in INST_TYPES for mp in INST_MAPS]
+                for suffix, ctype in INST_TYPES for mp in INST_MAPS + ([5, 6] if suffix == "f32" else [])]
         jobs += [(src, src.replace(".cu", ".o"), []) for src in SOURCES]
         results = list(ex.map(lambda j: compile_one(j, force, verbose, hdr_time), jobs))
     objs = [o for o, _ in results]

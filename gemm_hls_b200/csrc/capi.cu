@@ -27,6 +27,8 @@ int fail(int code, const std::string &msg) {
 struct mm_context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the pipelined host path
+  std::vector<cudaEvent_t> sync_events;                // untimed events ordering the three streams
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   mm::Scratch scratch;       // operand copies of the tensor-core path
   mm::Scratch staging[3];    // device A, B, C of mm_gemm_host
@@ -175,6 +177,8 @@ int mm_context_create(int device, mm_context **out) {
   mm_context *ctx = new mm_context();
   ctx->device = device;
   MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
   MM_CUDA_TRY(cudaEventCreate(&ctx->ev_start));
   MM_CUDA_TRY(cudaEventCreate(&ctx->ev_stop));
   *out = ctx;
@@ -190,6 +194,9 @@ int mm_context_destroy(mm_context *ctx) {
     if (s.ptr) cudaFree(s.ptr);
   }
   for (auto e : ctx->prof_events) cudaEventDestroy(e);
+  for (auto e : ctx->sync_events) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->copy_in);
+  cudaStreamDestroy(ctx->copy_out);
   cudaEventDestroy(ctx->ev_start);
   cudaEventDestroy(ctx->ev_stop);
   cudaStreamDestroy(ctx->stream);
@@ -333,27 +340,106 @@ int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flag
     ctx = g_default_ctx;
   }
   const auto t0 = std::chrono::high_resolution_clock::now();
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
   const size_t es = mm_dtype_size(dtype);
   const size_t bytes_a = size_t(n) * k * es, bytes_b = size_t(k) * m * es, bytes_c = size_t(n) * m * es;
-  void *da, *db, *dc;
-  {
-    std::lock_guard<std::mutex> lock(ctx->mutex);
-    MM_CUDA_TRY(cudaSetDevice(ctx->device));
-    if ((rc = ensure(ctx->staging[0], bytes_a)) != MM_OK) return rc;
-    if ((rc = ensure(ctx->staging[1], bytes_b)) != MM_OK) return rc;
-    if ((rc = ensure(ctx->staging[2], bytes_c)) != MM_OK) return rc;
-    da = ctx->staging[0].ptr;
-    db = ctx->staging[1].ptr;
-    dc = ctx->staging[2].ptr;
-    MM_CUDA_TRY(cudaMemcpyAsync(da, a, bytes_a, cudaMemcpyHostToDevice, ctx->stream));
-    MM_CUDA_TRY(cudaMemcpyAsync(db, b, bytes_b, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = ensure(ctx->staging[0], bytes_a)) != MM_OK) return rc;
+  if ((rc = ensure(ctx->staging[1], bytes_b)) != MM_OK) return rc;
+  if ((rc = ensure(ctx->staging[2], bytes_c)) != MM_OK) return rc;
+  unsigned char *da = static_cast<unsigned char *>(ctx->staging[0].ptr);
+  unsigned char *db = static_cast<unsigned char *>(ctx->staging[1].ptr);
+  unsigned char *dc = static_cast<unsigned char *>(ctx->staging[2].ptr);
+  const unsigned char *ha = static_cast<const unsigned char *>(a);
+  unsigned char *hc = static_cast<unsigned char *>(c);
+
+  // Row-chunk pipeline: C row-blocks are independent (kernel/Compute.cpp:53-56), so the H2D copy of
+  // A chunk i+1, the kernels of chunk i and the D2H copy of C chunk i-1 run concurrently on three
+  // streams; B is copied (and, on the tcgen05 path, prepared) once up front.  A stored K x N cannot
+  // be cut into contiguous row chunks: it takes the single-chunk route.
+  Path path = select_path(dtype, map_op, reduce_op, flags);
+  const bool ta = (flags & MM_FLAG_TRANSPOSED_A) != 0;
+  if (path == kPathDmma && ta && (n % 2 != 0)) path = kPathSemiring;
+  unsigned chunk_rows = n;
+  if (!ta) {
+    const size_t row_bytes = size_t(k) * es;
+    size_t rows = std::max<size_t>((n + 15) / 16, ((size_t(32) << 20) + row_bytes - 1) / row_bytes);
+    rows = (rows + 127) / 128 * 128;
+    if (rows < n) chunk_rows = unsigned(rows);
   }
-  rc = mm_kernel_execute(ctx, dtype, map_op, reduce_op, flags, da, db, dc, n, k, m, seconds_device, nullptr);
-  if (rc != MM_OK) return rc;
-  {
-    std::lock_guard<std::mutex> lock(ctx->mutex);
-    MM_CUDA_TRY(cudaMemcpyAsync(c, dc, bytes_c, cudaMemcpyDeviceToHost, ctx->stream));
-    MM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  const unsigned chunks = (n + chunk_rows - 1) / chunk_rows;
+  while (ctx->sync_events.size() < size_t(2 * chunks + 1)) {
+    cudaEvent_t e;
+    MM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->sync_events.push_back(e);
+  }
+  cudaEvent_t ev_b = ctx->sync_events[0];
+  auto ev_a = [&](unsigned i) { return ctx->sync_events[1 + i]; };
+  auto ev_c = [&](unsigned i) { return ctx->sync_events[1 + chunks + i]; };
+
+  // ---- H2D stream
+  MM_CUDA_TRY(cudaMemcpyAsync(db, b, bytes_b, cudaMemcpyHostToDevice, ctx->copy_in));
+  MM_CUDA_TRY(cudaEventRecord(ev_b, ctx->copy_in));
+  for (unsigned i = 0; i < chunks; ++i) {
+    const size_t r0 = size_t(i) * chunk_rows, rows = std::min<size_t>(chunk_rows, n - r0);
+    if (!ta) {
+      MM_CUDA_TRY(cudaMemcpyAsync(da + r0 * k * es, ha + r0 * k * es, rows * k * es, cudaMemcpyHostToDevice,
+                                  ctx->copy_in));
+    } else {
+      MM_CUDA_TRY(cudaMemcpyAsync(da, ha, bytes_a, cudaMemcpyHostToDevice, ctx->copy_in));
+    }
+    MM_CUDA_TRY(cudaEventRecord(ev_a(i), ctx->copy_in));
+  }
+
+  // ---- compute stream
+  void *bt = nullptr;
+  unsigned char *aprep = nullptr;
+  if (path == kPathTcgen05) {
+    if (flags & MM_FLAG_TF32X3) return fail(MM_ERR_UNSUPPORTED, "MM_FLAG_TF32X3 is not implemented yet");
+    if ((rc = ensure(ctx->scratch, mm::tcgen05_scratch_bytes(dtype, n, k, m, flags))) != MM_OK) return rc;
+    bt = ctx->scratch.ptr;
+    aprep = static_cast<unsigned char *>(ctx->scratch.ptr) + mm::tcgen05_bt_bytes(dtype, k, m);
+  }
+  MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev_b, 0));
+  MM_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
+  if (path == kPathTcgen05) {
+    if ((rc = mm::tcgen05_prepare_b(dtype, db, bt, k, m, ctx->stream)) != MM_OK) return rc;
+  }
+  for (unsigned i = 0; i < chunks; ++i) {
+    const size_t r0 = size_t(i) * chunk_rows, rows = std::min<size_t>(chunk_rows, n - r0);
+    MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev_a(i), 0));
+    const void *a_chunk = da + (ta ? 0 : r0 * k * es);
+    void *c_chunk = dc + r0 * m * es;
+    if (path == kPathTcgen05) {
+      const void *a_op = nullptr;
+      rc = mm::tcgen05_prepare_a(dtype, a_chunk, aprep + (ta ? 0 : r0 * k * es), unsigned(rows), k, ta, &a_op,
+                                 ctx->stream);
+      if (rc != MM_OK) return rc;
+      rc = mm::tcgen05_gemm(dtype, a_op, bt, c_chunk, unsigned(rows), k, m, ctx->stream);
+    } else {
+      mm::GemmArgs g{a_chunk, db, c_chunk, unsigned(rows), k, m, flags, ctx->stream};
+      rc = (path == kPathDmma) ? mm::launch_dmma(g) : mm::launch_semiring(dtype, map_op, reduce_op, g);
+    }
+    if (rc != MM_OK) return rc;
+    MM_CUDA_TRY(cudaEventRecord(ev_c(i), ctx->stream));
+  }
+  MM_CUDA_TRY(cudaEventRecord(ctx->ev_stop, ctx->stream));
+
+  // ---- D2H stream
+  for (unsigned i = 0; i < chunks; ++i) {
+    const size_t r0 = size_t(i) * chunk_rows, rows = std::min<size_t>(chunk_rows, n - r0);
+    MM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ev_c(i), 0));
+    MM_CUDA_TRY(cudaMemcpyAsync(hc + r0 * m * es, dc + r0 * m * es, rows * m * es, cudaMemcpyDeviceToHost,
+                                ctx->copy_out));
+  }
+  MM_CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
+  MM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (seconds_device) {
+    // first kernel start .. last kernel end on the compute stream (with more than one chunk this
+    // includes the stalls waiting for A chunks to arrive)
+    float ms = 0.f;
+    MM_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+    *seconds_device = 1e-3 * ms;
   }
   if (seconds_wall) {
     *seconds_wall = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();

@@ -4,7 +4,7 @@
 // B200 counterpart of the reference's PE chain for MM_DATA_TYPE=double
 // (kernel/Compute.cpp:53-146; README.md:8 quotes 132 GFLOP/s for it on a VCU1525).
 //
-// CTA tile 128 x 128, BK = 16, 256 threads = 8 warps as 2 (rows) x 4 (cols), warp tile 64 x 32 =
+// CTA tile 128 x 128, BK = 32, 256 threads = 8 warps as 2 (rows) x 4 (cols), warp tile 64 x 32 =
 // 8 x 4 m8n8 accumulator tiles (64 doubles per thread).  A and B tiles keep their global
 // orientation in shared memory; row pitches are padded by 4 doubles so that the 8-byte fragment
 // reads of each half-warp hit 16 distinct 8-byte banks.
@@ -17,7 +17,7 @@
 namespace mm {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int STAGES = 3;
 constexpr int LDA_S = BK + 4;   // As[BM][LDA_S]   (A row-major tile)
 constexpr int LDAT_S = BM + 4;  // AsT[BK][LDAT_S] (A stored K x N)
@@ -65,11 +65,11 @@ gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, dou
     double *as = As + stage * A_TILE;
     double *bs = Bs + stage * B_TILE;
     if (!TRANSPOSED_A) {
-      // 128 rows x 16 doubles = 1024 16-byte chunks; 8 chunks per row
+      // 128 rows x BK doubles as 16-byte chunks; BK / 2 chunks per row
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < BM * BK / 2 / 256; ++i) {
         const int c = tid + i * 256;
-        const int r = c / 8, part = c % 8;
+        const int r = c / (BK / 2), part = c % (BK / 2);
         size_t row = row0 + r;
         if (row >= size_n) row = size_n - 1;
         const unsigned kk = k0 + part * 2;
@@ -77,9 +77,9 @@ gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, dou
         cp_async16(as + r * LDA_S + part * 2, A + row * size_k + (valid ? kk : 0), valid);
       }
     } else {
-      // 16 k-rows x 128 n-cols; 64 chunks per row
+      // BK k-rows x 128 n-cols; 64 chunks per row
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < BK * BM / 2 / 256; ++i) {
         const int c = tid + i * 256;
         const int kk = c / 64, part = c % 64;
         size_t n = row0 + part * 2;
@@ -89,7 +89,7 @@ gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, dou
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < BK * BN / 2 / 256; ++i) {
       const int c = tid + i * 256;
       const int kk = c / 64, part = c % 64;
       size_t col = col0 + part * 2;

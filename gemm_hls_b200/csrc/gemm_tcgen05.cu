@@ -34,27 +34,39 @@
 namespace mm {
 namespace {
 
-constexpr int BLOCK_M = 128;          // C rows per tile  (UMMA M)
-constexpr int BLOCK_N = 256;          // C cols per tile  (UMMA N)
+constexpr int BLOCK_M = 128;          // C rows per CTA      (UMMA M = 128 * CTA group size)
+constexpr int BLOCK_N = 256;          // C cols per tile     (UMMA N)
 constexpr int BLOCK_K_BYTES = 128;    // one 128-byte swizzle atom of K per stage
 constexpr int UMMA_K_BYTES = 32;      // K extent of one tcgen05.mma
-constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K_BYTES;  // 16 KiB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K_BYTES;  // 32 KiB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;
-constexpr int RASTER_GROUP = 16;  // row-tiles per rasterisation group (L2 reuse of B^T tiles)
-constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int RASTER_GROUP_ROWS = 2048;  // C rows per rasterisation group (L2 reuse of B^T panels)
+
+// Per-variant geometry.  CG = 1: one CTA computes a 128 x 256 tile and stages A (128 rows) + B^T
+// (256 rows) per k-block.  CG = 2 (cta_group::2): a CTA PAIR computes 256 x 256 with ONE
+// tcgen05.mma per k-step issued by the leader CTA; each CTA stages only its own 128 A rows and its
+// half (128 rows) of the B^T tile, so per-SM shared-memory fill and L2 traffic drop by a third and
+// the freed shared memory deepens the ring from 4 to 6 stages.
+template <int CG>
+struct Geo {
+  static constexpr int LOAD_N = BLOCK_N / CG;                       // B^T rows staged per CTA
+  static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K_BYTES;     // 16 KiB
+  static constexpr int B_STAGE_BYTES = LOAD_N * BLOCK_K_BYTES;      // 32 / 16 KiB
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (CG == 1) ? 4 : 6;
+  static constexpr int TILE_ROWS = BLOCK_M * CG;                    // C rows per CTA group
+  static constexpr int RASTER_GROUP = RASTER_GROUP_ROWS / TILE_ROWS;
+  static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct TileCoord {
   uint32_t r, c;
 };
 
-// Grouped rasterisation: RASTER_GROUP row-tiles sweep all column-tiles together so that the ~148
+// Grouped rasterisation: RASTER_GROUP row-tiles sweep all column-tiles together so that the
 // concurrently running tiles share A row-panels and B column-panels through L2.
+template <int RASTER_GROUP>
 __device__ __forceinline__ TileCoord tile_coord(uint32_t t, uint32_t tiles_r, uint32_t tiles_c) {
   const uint32_t per_group = RASTER_GROUP * tiles_c;
   const uint32_t g = t / per_group;
@@ -96,80 +108,111 @@ __device__ __forceinline__ void store_chunk<__half>(__half *crow, const uint32_t
   }
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // C[rows x cols] = A'[rows x k] * Bt[cols x k]^T ; A', Bt K-major, described by the tensor maps.
-template <int KIND, typename TOut>
+// CG == 2 must be launched with cluster dimension (2, 1, 1).
+template <int KIND, typename TOut, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, TOut *__restrict__ C, uint32_t rows,
                     uint32_t cols, uint32_t k_bytes) {
+  using G = Geo<CG>;
+  constexpr int STAGES = G::STAGES;
   extern __shared__ unsigned char smem_raw[];
-  // 128B-swizzled tiles must start on a 1024-byte boundary.
+  // 128B-swizzled tiles must start on a 1024-byte boundary (same offset in both CTAs of a pair).
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a0 = smem_base;
-  const uint32_t smem_b0 = smem_base + STAGES * A_STAGE_BYTES;
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t smem_b0 = smem_base + STAGES * G::A_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * G::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + ACC_STAGES + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC_STAGES);
-  // generic pointer to the TMEM base slot
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(
       smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const uint32_t warp = threadIdx.x / 32;
   const uint32_t lane = threadIdx.x % 32;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  const uint32_t group_id = blockIdx.x / CG;
+  const uint32_t num_groups = gridDim.x / CG;
 
-  const uint32_t tiles_r = (rows + BLOCK_M - 1) / BLOCK_M;
+  const uint32_t tiles_r = (rows + G::TILE_ROWS - 1) / G::TILE_ROWS;
   const uint32_t tiles_c = (cols + BLOCK_N - 1) / BLOCK_N;
   const uint32_t num_tiles = tiles_r * tiles_c;
   const uint32_t num_kb = (k_bytes + BLOCK_K_BYTES - 1) / BLOCK_K_BYTES;
   constexpr int ELEM_BYTES = (KIND == ptx::KIND_TF32) ? 4 : 2;
   constexpr int BLOCK_K_ELEMS = BLOCK_K_BYTES / ELEM_BYTES;
 
+  if (CG == 2) cluster_sync_all();  // both CTAs resident before the pair-wide TMEM allocation
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), 1);   // producer's arrive.expect_tx
-      ptx::mbar_init(empty_bar(s), 1);  // tcgen05.commit
+      ptx::mbar_init(full_bar(s), CG);  // one producer arrival per CTA of the group (leader's copy is used)
+      ptx::mbar_init(empty_bar(s), 1);  // tcgen05.commit (multicast to both CTAs when CG == 2)
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
-      ptx::mbar_init(tmem_full_bar(s), 1);   // tcgen05.commit
-      ptx::mbar_init(tmem_empty_bar(s), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(tmem_full_bar(s), 1);        // tcgen05.commit
+      ptx::mbar_init(tmem_empty_bar(s), 4 * CG);  // one arrive per epilogue warp of the group (leader's copy)
     }
     ptx::fence_mbar_init();
   } else if (warp == 1) {
-    ptx::tmem_alloc<1>(tmem_slot, TMEM_COLS);
+    ptx::tmem_alloc<CG>(tmem_slot, TMEM_COLS);
   }
   ptx::tcgen05_fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   ptx::tcgen05_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (one per CTA) =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(t, tiles_r, tiles_c);
+      for (uint32_t t = group_id; t < num_tiles; t += num_groups) {
+        const TileCoord tc = tile_coord<G::RASTER_GROUP>(t, tiles_r, tiles_c);
+        const int32_t a_row = tc.r * G::TILE_ROWS + cta_rank * BLOCK_M;
+        const int32_t b_row = tc.c * BLOCK_N + cta_rank * G::LOAD_N;
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-          ptx::mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          ptx::tma_load_2d(smem_a0 + stage * A_STAGE_BYTES, &tmap_a, full_bar(stage),
-                           kb * BLOCK_K_ELEMS, tc.r * BLOCK_M);
-          ptx::tma_load_2d(smem_b0 + stage * B_STAGE_BYTES, &tmap_b, full_bar(stage),
-                           kb * BLOCK_K_ELEMS, tc.c * BLOCK_N);
+          if (CG == 1) {
+            ptx::mbar_arrive_expect_tx(full_bar(stage), G::STAGE_BYTES);
+            ptx::tma_load_2d(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, full_bar(stage),
+                             kb * BLOCK_K_ELEMS, a_row);
+            ptx::tma_load_2d(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, full_bar(stage),
+                             kb * BLOCK_K_ELEMS, b_row);
+          } else {
+            // both CTAs' bytes are accounted on the LEADER's barrier (peer bit 24 cleared)
+            const uint32_t leader_bar = full_bar(stage) & 0xFEFFFFFFu;
+            if (cta_rank == 0) {
+              ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * G::STAGE_BYTES);
+            } else {
+              ptx::mbar_arrive_cluster(full_bar(stage), 0);
+            }
+            ptx::tma_load_2d_2sm(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, leader_bar,
+                                 kb * BLOCK_K_ELEMS, a_row);
+            ptx::tma_load_2d_2sm(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, leader_bar,
+                                 kb * BLOCK_K_ELEMS, b_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc(KIND, BLOCK_M, BLOCK_N);
+    // ================= MMA issuer (leader CTA only) =================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc(KIND, BLOCK_M * CG, BLOCK_N);
       uint32_t stage = 0, phase = 0, iter = 0;
-      for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++iter) {
+      for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++iter) {
         const uint32_t as = iter & 1u;
         const uint32_t aphase = (iter >> 1) & 1u;
         ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1);
@@ -178,32 +221,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tcgen05_fence_after_sync();
-          const uint64_t adesc = ptx::make_smem_desc_k_sw128(smem_a0 + stage * A_STAGE_BYTES);
-          const uint64_t bdesc = ptx::make_smem_desc_k_sw128(smem_b0 + stage * B_STAGE_BYTES);
+          const uint64_t adesc = ptx::make_smem_desc_k_sw128(smem_a0 + stage * G::A_STAGE_BYTES);
+          const uint64_t bdesc = ptx::make_smem_desc_k_sw128(smem_b0 + stage * G::B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K_BYTES / UMMA_K_BYTES; ++k) {
             // advancing K inside the swizzle atom = advancing the start address (>>4 units)
-            ptx::umma<KIND, 1>(tmem_d, adesc + uint64_t(k * (UMMA_K_BYTES >> 4)),
-                               bdesc + uint64_t(k * (UMMA_K_BYTES >> 4)), idesc,
-                               (kb | uint32_t(k)) != 0u ? 1u : 0u);
+            ptx::umma<KIND, CG>(tmem_d, adesc + uint64_t(k * (UMMA_K_BYTES >> 4)),
+                                bdesc + uint64_t(k * (UMMA_K_BYTES >> 4)), idesc,
+                                (kb | uint32_t(k)) != 0u ? 1u : 0u);
           }
-          ptx::umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit(tmem_full_bar(as));
+          // smem stage reusable / accumulator complete once these MMAs retire
+          if (CG == 1) {
+            ptx::umma_commit(empty_bar(stage));
+            if (kb == num_kb - 1) ptx::umma_commit(tmem_full_bar(as));
+          } else {
+            ptx::umma_commit_2sm(empty_bar(stage), 0x3);
+            if (kb == num_kb - 1) ptx::umma_commit_2sm(tmem_full_bar(as), 0x3);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..5 of every CTA) =================
     const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, +32) are this warp's
     uint32_t iter = 0;
-    for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++iter) {
-      const TileCoord tc = tile_coord(t, tiles_r, tiles_c);
+    for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++iter) {
+      const TileCoord tc = tile_coord<G::RASTER_GROUP>(t, tiles_r, tiles_c);
       const uint32_t as = iter & 1u;
       const uint32_t aphase = (iter >> 1) & 1u;
       ptx::mbar_wait(tmem_full_bar(as), aphase);
       ptx::tcgen05_fence_after_sync();
-      const uint32_t row = tc.r * BLOCK_M + quarter * 32 + lane;
+      const uint32_t row = tc.r * G::TILE_ROWS + cta_rank * BLOCK_M + quarter * 32 + lane;
       TOut *crow = C + size_t(row) * cols;
       const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + as * BLOCK_N;
 #pragma unroll 1
@@ -215,15 +264,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       ptx::tcgen05_fence_before_sync();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));
+      if (lane == 0) {
+        if (CG == 1) ptx::mbar_arrive(tmem_empty_bar(as));
+        else ptx::mbar_arrive_cluster(tmem_empty_bar(as), 0);  // the leader's MMA issuer waits on it
+      }
     }
   }
 
   ptx::tcgen05_fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     ptx::tcgen05_fence_after_sync();
-    ptx::tmem_dealloc<1>(tmem_base, TMEM_COLS);
+    ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);
   }
 }
 
@@ -345,11 +397,121 @@ void launch_transpose(const void *src, void *dst, uint32_t src_rows, uint32_t sr
 
 }  // namespace
 
+size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m) {
+  const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  return align_up(size_t(m) * k * eb, 1024);
+}
+
 size_t tcgen05_scratch_bytes(int dtype, unsigned n, unsigned k, unsigned m, int flags) {
   const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
-  size_t bytes = align_up(size_t(m) * k * eb, 1024);  // B^T
+  size_t bytes = tcgen05_bt_bytes(dtype, k, m);  // B^T
   if (dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) bytes += align_up(size_t(n) * k * eb, 1024);
   return bytes;
+}
+
+// Experiment hook (scripts/exp_tf32_rounding.py): feed raw fp32 bits to kind::tf32 to MEASURE the
+// truncation bias that motivates the rounding pass.  Never set in production.
+static bool experiment_no_round() {
+  static const bool v = std::getenv("MM_EXPERIMENT_TF32_NO_ROUND") != nullptr;
+  return v;
+}
+
+// B (row-major K x M) -> B^T (M x K, K-major MMA operand) into `bt`; float is rounded to TF32.
+int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m, cudaStream_t stream) {
+  if (dtype == MM_DTYPE_FLOAT) {
+    if (experiment_no_round()) {
+      launch_transpose<float, false>(b, bt, k, m, stream);
+    } else {
+      launch_transpose<float, true>(b, bt, k, m, stream);
+    }
+  } else {
+    launch_transpose<__half, false>(b, bt, k, m, stream);
+  }
+  MM_CUDA_TRY(cudaGetLastError());
+  return MM_OK;
+}
+
+// `rows` rows of A -> the K-major A operand.  Row-major float A is rounded into `aprep`; row-major
+// half A is used in place; A stored K x N (`transposed`, leading dimension n_total, only whole
+// matrices) is transposed into `aprep`.  *a_op receives the operand pointer.
+int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, bool transposed,
+                      const void **a_op, cudaStream_t stream) {
+  *a_op = a;
+  if (dtype == MM_DTYPE_FLOAT) {
+    if (transposed) {
+      if (experiment_no_round()) {
+        launch_transpose<float, false>(a, aprep, k, rows, stream);
+      } else {
+        launch_transpose<float, true>(a, aprep, k, rows, stream);  // A stored K x N -> N x K
+      }
+      *a_op = aprep;
+    } else if (!experiment_no_round()) {
+      const size_t count4 = size_t(rows) * k / 4;
+      const int blocks = int(std::min<size_t>((count4 + 255) / 256, size_t(num_sms()) * 16));
+      round_tf32_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float4 *>(a),
+                                                   static_cast<float4 *>(aprep), count4);
+      *a_op = aprep;
+    }
+  } else if (transposed) {
+    launch_transpose<__half, false>(a, aprep, k, rows, stream);
+    *a_op = aprep;
+  }
+  MM_CUDA_TRY(cudaGetLastError());
+  return MM_OK;
+}
+
+// 1 = single-CTA tiles, 2 = cta_group::2 CTA pairs (default).  MM_TCGEN05_CTA_GROUP overrides for A/B runs.
+static int cta_group_choice() {
+  static const int v = [] {
+    const char *e = std::getenv("MM_TCGEN05_CTA_GROUP");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  return v;
+}
+
+template <int KIND, typename TOut, int CG>
+static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_b, void *c, unsigned rows,
+                               unsigned m, uint32_t k_bytes, cudaStream_t stream) {
+  using G = Geo<CG>;
+  auto kern = gemm_tcgen05_kernel<KIND, TOut, CG>;
+  MM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G::SMEM_BYTES)));
+  const uint32_t tiles = ceil_div(rows, G::TILE_ROWS) * ceil_div(m, BLOCK_N);
+  const uint32_t groups = std::min<uint32_t>(tiles, uint32_t(num_sms()) / CG);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CG);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = G::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, static_cast<TOut *>(c), uint32_t(rows), uint32_t(m),
+                                 k_bytes));
+  return MM_OK;
+}
+
+// C[rows x m] = Aop[rows x k] * Bt[m x k]^T on the tensor cores.
+int tcgen05_gemm(int dtype, const void *a_op, const void *bt, void *c, unsigned rows, unsigned k,
+                 unsigned m, cudaStream_t stream) {
+  const bool is_f32 = dtype == MM_DTYPE_FLOAT;
+  const size_t eb = is_f32 ? 4 : 2;
+  const int cg = cta_group_choice();
+  CUtensorMap map_a, map_b;
+  int rc = make_operand_map(&map_a, a_op, dtype, rows, k, BLOCK_M);
+  if (rc != MM_OK) return rc;
+  rc = make_operand_map(&map_b, bt, dtype, m, k, cg == 2 ? Geo<2>::LOAD_N : Geo<1>::LOAD_N);
+  if (rc != MM_OK) return rc;
+  const uint32_t k_bytes = uint32_t(size_t(k) * eb);
+  if (is_f32) {
+    return cg == 2 ? launch_gemm_variant<ptx::KIND_TF32, float, 2>(map_a, map_b, c, rows, m, k_bytes, stream)
+                   : launch_gemm_variant<ptx::KIND_TF32, float, 1>(map_a, map_b, c, rows, m, k_bytes, stream);
+  }
+  return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2>(map_a, map_b, c, rows, m, k_bytes, stream)
+                 : launch_gemm_variant<ptx::KIND_F16, __half, 1>(map_a, map_b, c, rows, m, k_bytes, stream);
 }
 
 int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_bytes) {
@@ -357,71 +519,21 @@ int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_b
     return fail(MM_ERR_UNSUPPORTED, "tcgen05 path handles float and half only");
   }
   if (g.flags & MM_FLAG_TF32X3) return fail(MM_ERR_UNSUPPORTED, "MM_FLAG_TF32X3 is not implemented yet");
-  const bool is_f32 = dtype == MM_DTYPE_FLOAT;
   const bool ta = (g.flags & MM_FLAG_TRANSPOSED_A) != 0;
-  const size_t eb = is_f32 ? 4 : 2;
   if (scratch_bytes < tcgen05_scratch_bytes(dtype, g.n, g.k, g.m, g.flags)) {
     return fail(MM_ERR_INVALID, "tcgen05 scratch too small");
   }
   unsigned char *sp = static_cast<unsigned char *>(scratch);
   void *bt = sp;
-  void *aprep = sp + align_up(size_t(g.m) * g.k * eb, 1024);
+  void *aprep = sp + tcgen05_bt_bytes(dtype, g.k, g.m);
 
-  // ---- operand preparation ----
-  const void *a_op = g.a;
-  // Experiment hook (scripts/exp_tf32_rounding.py): feed raw fp32 bits to kind::tf32 to MEASURE the
-  // truncation bias that motivates the rounding pass.  Never set in production.
-  static const bool no_round = std::getenv("MM_EXPERIMENT_TF32_NO_ROUND") != nullptr;
-  if (is_f32 && no_round) {
-    launch_transpose<float, false>(g.b, bt, g.k, g.m, g.stream);
-    if (ta) {
-      launch_transpose<float, false>(g.a, aprep, g.k, g.n, g.stream);
-      a_op = aprep;
-    }
-  } else if (is_f32) {
-    launch_transpose<float, true>(g.b, bt, g.k, g.m, g.stream);  // B (K x M) -> B^T (M x K), rounded
-    if (ta) {
-      launch_transpose<float, true>(g.a, aprep, g.k, g.n, g.stream);  // A stored K x N -> N x K
-    } else {
-      const size_t count4 = size_t(g.n) * g.k / 4;
-      const int blocks = int(std::min<size_t>((count4 + 255) / 256, size_t(num_sms()) * 16));
-      round_tf32_kernel<<<blocks, 256, 0, g.stream>>>(static_cast<const float4 *>(g.a),
-                                                     static_cast<float4 *>(aprep), count4);
-    }
-    a_op = aprep;
-  } else {
-    launch_transpose<__half, false>(g.b, bt, g.k, g.m, g.stream);
-    if (ta) {
-      launch_transpose<__half, false>(g.a, aprep, g.k, g.n, g.stream);
-      a_op = aprep;
-    }
-  }
-  MM_CUDA_TRY(cudaGetLastError());
+  int rc = tcgen05_prepare_b(dtype, g.b, bt, g.k, g.m, g.stream);
+  if (rc != MM_OK) return rc;
+  const void *a_op = nullptr;
+  rc = tcgen05_prepare_a(dtype, g.a, aprep, g.n, g.k, ta, &a_op, g.stream);
+  if (rc != MM_OK) return rc;
   if (g.ev_prep_done) MM_CUDA_TRY(cudaEventRecord(g.ev_prep_done, g.stream));
-
-  // ---- tensor maps + GEMM ----
-  CUtensorMap map_a, map_b;
-  int rc = make_operand_map(&map_a, a_op, dtype, g.n, g.k, BLOCK_M);
-  if (rc != MM_OK) return rc;
-  rc = make_operand_map(&map_b, bt, dtype, g.m, g.k, BLOCK_N);
-  if (rc != MM_OK) return rc;
-
-  const uint32_t tiles = ceil_div(g.n, BLOCK_M) * ceil_div(g.m, BLOCK_N);
-  const uint32_t grid = std::min<uint32_t>(tiles, uint32_t(num_sms()));
-  const uint32_t k_bytes = uint32_t(size_t(g.k) * eb);
-  if (is_f32) {
-    auto kern = gemm_tcgen05_kernel<ptx::KIND_TF32, float>;
-    MM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, g.stream>>>(map_a, map_b, static_cast<float *>(g.c), g.n,
-                                                     g.m, k_bytes);
-  } else {
-    auto kern = gemm_tcgen05_kernel<ptx::KIND_F16, __half>;
-    MM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-    kern<<<grid, NUM_THREADS, SMEM_BYTES, g.stream>>>(map_a, map_b, static_cast<__half *>(g.c), g.n,
-                                                     g.m, k_bytes);
-  }
-  MM_CUDA_TRY(cudaGetLastError());
-  return MM_OK;
+  return tcgen05_gemm(dtype, a_op, bt, g.c, g.n, g.k, g.m, g.stream);
 }
 
 }  // namespace mm

@@ -18,6 +18,15 @@ int by_map(int map_op, int reduce_op, const GemmArgs &g, bool ta) {
   return -1;
 }
 
+// float only: the hardware min/max variants (internal operator codes)
+int by_map_float(int map_op, int reduce_op, const GemmArgs &g, bool ta) {
+  switch (map_op) {
+    case MM_OP_MIN_FAST: return launch_semiring_for<float, MM_OP_MIN_FAST>(reduce_op, g.a, g.b, g.c, g.n, g.k, g.m, ta, g.stream);
+    case MM_OP_MAX_FAST: return launch_semiring_for<float, MM_OP_MAX_FAST>(reduce_op, g.a, g.b, g.c, g.n, g.k, g.m, ta, g.stream);
+  }
+  return by_map<float>(map_op, reduce_op, g, ta);
+}
+
 }  // namespace
 
 int launch_semiring(int dtype, int map_op, int reduce_op, const GemmArgs &g) {
@@ -25,7 +34,15 @@ int launch_semiring(int dtype, int map_op, int reduce_op, const GemmArgs &g) {
   int rc = -1;
   switch (dtype) {
     case MM_DTYPE_HALF: rc = by_map<__half>(map_op, reduce_op, g, ta); break;
-    case MM_DTYPE_FLOAT: rc = by_map<float>(map_op, reduce_op, g, ta); break;
+    case MM_DTYPE_FLOAT: {
+      // Min / Max on float use FMNMX unless the caller asked for the literal C++ semantics
+      auto fast = [&](int op) {
+        if (g.flags & MM_FLAG_EXACT) return op;
+        return op == MM_OP_MIN ? int(MM_OP_MIN_FAST) : (op == MM_OP_MAX ? int(MM_OP_MAX_FAST) : op);
+      };
+      rc = by_map_float(fast(map_op), fast(reduce_op), g, ta);
+      break;
+    }
     case MM_DTYPE_DOUBLE: rc = by_map<double>(map_op, reduce_op, g, ta); break;
     case MM_DTYPE_INT32: rc = by_map<int>(map_op, reduce_op, g, ta); break;
     case MM_DTYPE_UINT32: rc = by_map<unsigned>(map_op, reduce_op, g, ta); break;

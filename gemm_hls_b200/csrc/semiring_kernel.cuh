@@ -21,6 +21,8 @@
 
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "semiring.cuh"
 
 namespace mm {
@@ -150,24 +152,32 @@ semiring_tile_kernel(const T *__restrict__ A, const T *__restrict__ B, T *__rest
     const T *as = As + buf * BK * LDA;
     const T *bs = Bs + buf * BK * LDB;
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      Quad<T> a0 = *reinterpret_cast<const Quad<T> *>(as + kk * LDA + ty * 4);
-      Quad<T> a1 = *reinterpret_cast<const Quad<T> *>(as + kk * LDA + 64 + ty * 4);
-      Quad<T> b0 = *reinterpret_cast<const Quad<T> *>(bs + kk * LDB + tx * 4);
-      Quad<T> b1 = *reinterpret_cast<const Quad<T> *>(bs + kk * LDB + 64 + tx * 4);
-      T af[8], bf[8];
+    for (int kk = 0; kk < BK; kk += 2) {
+      // two consecutive k per step, reduced in order inside ONE expression
+      //   acc = Reduce(Reduce(acc, Map(a_k, b_k)), Map(a_k+1, b_k+1))
+      // so that a 3-input hardware reduction (FMNMX3 for float min/max) can be selected; the
+      // evaluation order, and therefore every rounding, is the sequential order of Naive<>.
+      T af[2][8], bf[2][8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        af[q] = a0.v[q];
-        af[4 + q] = a1.v[q];
-        bf[q] = b0.v[q];
-        bf[4 + q] = b1.v[q];
+      for (int u = 0; u < 2; ++u) {
+        const Quad<T> a0 = *reinterpret_cast<const Quad<T> *>(as + (kk + u) * LDA + ty * 4);
+        const Quad<T> a1 = *reinterpret_cast<const Quad<T> *>(as + (kk + u) * LDA + 64 + ty * 4);
+        const Quad<T> b0 = *reinterpret_cast<const Quad<T> *>(bs + (kk + u) * LDB + tx * 4);
+        const Quad<T> b1 = *reinterpret_cast<const Quad<T> *>(bs + (kk + u) * LDB + 64 + tx * 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          af[u][q] = a0.v[q];
+          af[u][4 + q] = a1.v[q];
+          bf[u][q] = b0.v[q];
+          bf[u][4 + q] = b1.v[q];
+        }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          acc[i][j] = Reduce::Apply(acc[i][j], Map::Apply(af[i], bf[j]));
+          acc[i][j] = Reduce::Apply(Reduce::Apply(acc[i][j], Map::Apply(af[0][i], bf[0][j])),
+                                    Map::Apply(af[1][i], bf[1][j]));
         }
       }
     }
@@ -232,6 +242,10 @@ int launch_semiring_for(int reduce_op, const void *a, const void *b, void *c, un
     MM_SEMIRING_CASE(MM_OP_MIN)                                                                    \
     MM_SEMIRING_CASE(MM_OP_MAX)                                                                    \
     MM_SEMIRING_CASE(MM_OP_AND)                                                                    \
+    if constexpr (std::is_same<T, float>::value) {                                                 \
+      MM_SEMIRING_CASE(MM_OP_MIN_FAST)                                                             \
+      MM_SEMIRING_CASE(MM_OP_MAX_FAST)                                                             \
+    }                                                                                              \
     return -1;                                                                                     \
   }
 
