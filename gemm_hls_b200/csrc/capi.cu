@@ -395,15 +395,14 @@ int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flag
   void *bt = nullptr;
   unsigned char *aprep = nullptr;
   if (path == kPathTcgen05) {
-    if (flags & MM_FLAG_TF32X3) return fail(MM_ERR_UNSUPPORTED, "MM_FLAG_TF32X3 is not implemented yet");
     if ((rc = ensure(ctx->scratch, mm::tcgen05_scratch_bytes(dtype, n, k, m, flags))) != MM_OK) return rc;
     bt = ctx->scratch.ptr;
-    aprep = static_cast<unsigned char *>(ctx->scratch.ptr) + mm::tcgen05_bt_bytes(dtype, k, m);
+    aprep = static_cast<unsigned char *>(ctx->scratch.ptr) + mm::tcgen05_bt_bytes(dtype, k, m, flags);
   }
   MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev_b, 0));
   MM_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
   if (path == kPathTcgen05) {
-    if ((rc = mm::tcgen05_prepare_b(dtype, db, bt, k, m, ctx->stream)) != MM_OK) return rc;
+    if ((rc = mm::tcgen05_prepare_b(dtype, db, bt, k, m, flags, ctx->stream)) != MM_OK) return rc;
   }
   for (unsigned i = 0; i < chunks; ++i) {
     const size_t r0 = size_t(i) * chunk_rows, rows = std::min<size_t>(chunk_rows, n - r0);
@@ -412,10 +411,11 @@ int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flag
     void *c_chunk = dc + r0 * m * es;
     if (path == kPathTcgen05) {
       const void *a_op = nullptr;
-      rc = mm::tcgen05_prepare_a(dtype, a_chunk, aprep + (ta ? 0 : r0 * k * es), unsigned(rows), k, ta, &a_op,
-                                 ctx->stream);
+      const size_t a_scale = (dtype == MM_DTYPE_FLOAT && (flags & MM_FLAG_TF32X3)) ? 3 : 1;
+      rc = mm::tcgen05_prepare_a(dtype, a_chunk, aprep + (ta ? 0 : r0 * k * es * a_scale), unsigned(rows), k, flags,
+                                 &a_op, ctx->stream);
       if (rc != MM_OK) return rc;
-      rc = mm::tcgen05_gemm(dtype, a_op, bt, c_chunk, unsigned(rows), k, m, ctx->stream);
+      rc = mm::tcgen05_gemm(dtype, a_op, bt, c_chunk, unsigned(rows), k, m, flags, ctx->stream);
     } else {
       mm::GemmArgs g{a_chunk, db, c_chunk, unsigned(rows), k, m, flags, ctx->stream};
       rc = (path == kPathDmma) ? mm::launch_dmma(g) : mm::launch_semiring(dtype, map_op, reduce_op, g);

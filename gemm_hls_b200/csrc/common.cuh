@@ -51,15 +51,16 @@ int launch_semiring(int dtype, int map_op, int reduce_op, const GemmArgs &args);
 // tcgen05 tensor-core GEMM for (Multiply, Add) float (kind::tf32) and half (kind::f16).
 // `scratch_a` / `scratch_b` hold the K-major operand copies.  gemm_tcgen05.cu
 size_t tcgen05_scratch_bytes(int dtype, unsigned n, unsigned k, unsigned m, int flags);
-size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m);  // offset of the A operand copy in scratch
+size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m, int flags);  // offset of the A operand copy in scratch
 int launch_tcgen05(int dtype, const GemmArgs &args, void *scratch, size_t scratch_bytes);
 // The three phases of launch_tcgen05, for callers that reuse a prepared B across row-blocks
 // (the pipelined host path, multi-GPU row-block drivers):
-int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m, cudaStream_t stream);
-int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, bool transposed,
+int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m, int flags,
+                      cudaStream_t stream);
+int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, int flags,
                       const void **a_op, cudaStream_t stream);
 int tcgen05_gemm(int dtype, const void *a_op, const void *bt, void *c, unsigned rows, unsigned k,
-                 unsigned m, cudaStream_t stream);
+                 unsigned m, int flags, cudaStream_t stream);
 
 // DMMA (mma.sync m8n8k4 f64) GEMM for (Multiply, Add) double.  gemm_dmma.cu
 int launch_dmma(const GemmArgs &args);

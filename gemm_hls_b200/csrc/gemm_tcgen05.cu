@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -123,7 +124,7 @@ template <int KIND, typename TOut, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, TOut *__restrict__ C, uint32_t rows,
-                    uint32_t cols, uint32_t k_bytes) {
+                    uint32_t cols, uint32_t k_bytes, unsigned long long *dbg) {
   using G = Geo<CG>;
   constexpr int STAGES = G::STAGES;
   extern __shared__ unsigned char smem_raw[];
@@ -158,7 +159,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar(s), CG);  // one producer arrival per CTA of the group (leader's copy is used)
+      // ONE arrival: the (leader's) producer's arrive.expect_tx, which books the bytes of BOTH CTAs.
+      // The peer's TMA transactions complete_tx on the leader's barrier; no peer arrival is needed
+      // (a remote mbarrier.arrive per k-block stalled the peer's producer for ~400 cycles: measured
+      // with MM_TCGEN05_DEBUG, the MMA thread waited 68 % of the time on data).  The phase cannot
+      // complete early because the expected byte count includes the peer's half, and the peer
+      // cannot run a phase ahead because its empty barrier is released by the same tcgen05.commit.
+      ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);  // tcgen05.commit (multicast to both CTAs when CG == 2)
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
@@ -178,12 +185,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ================= TMA producer (one per CTA) =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      long long wait_empty = 0, t_begin = clock64();
       for (uint32_t t = group_id; t < num_tiles; t += num_groups) {
         const TileCoord tc = tile_coord<G::RASTER_GROUP>(t, tiles_r, tiles_c);
         const int32_t a_row = tc.r * G::TILE_ROWS + cta_rank * BLOCK_M;
         const int32_t b_row = tc.c * BLOCK_N + cta_rank * G::LOAD_N;
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+          if (dbg) {
+            const long long t0 = clock64();
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+            wait_empty += clock64() - t0;
+          } else {
+            ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+          }
           if (CG == 1) {
             ptx::mbar_arrive_expect_tx(full_bar(stage), G::STAGE_BYTES);
             ptx::tma_load_2d(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, full_bar(stage),
@@ -193,11 +207,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           } else {
             // both CTAs' bytes are accounted on the LEADER's barrier (peer bit 24 cleared)
             const uint32_t leader_bar = full_bar(stage) & 0xFEFFFFFFu;
-            if (cta_rank == 0) {
-              ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * G::STAGE_BYTES);
-            } else {
-              ptx::mbar_arrive_cluster(full_bar(stage), 0);
-            }
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * G::STAGE_BYTES);
             ptx::tma_load_2d_2sm(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, leader_bar,
                                  kb * BLOCK_K_ELEMS, a_row);
             ptx::tma_load_2d_2sm(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, leader_bar,
@@ -206,20 +216,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (dbg) {
+        dbg[blockIdx.x * 8 + 0] = wait_empty;
+        dbg[blockIdx.x * 8 + 1] = clock64() - t_begin;
+      }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = ptx::make_idesc(KIND, BLOCK_M * CG, BLOCK_N);
       uint32_t stage = 0, phase = 0, iter = 0;
+      long long wait_full = 0, wait_tmem = 0, t_begin = clock64();
       for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++iter) {
         const uint32_t as = iter & 1u;
         const uint32_t aphase = (iter >> 1) & 1u;
-        ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1);
+        if (dbg) {
+          const long long t0 = clock64();
+          ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1);
+          wait_tmem += clock64() - t0;
+        } else {
+          ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1);
+        }
         ptx::tcgen05_fence_after_sync();
         const uint32_t tmem_d = tmem_base + as * BLOCK_N;
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(full_bar(stage), phase);
+          if (dbg) {
+            const long long t0 = clock64();
+            ptx::mbar_wait(full_bar(stage), phase);
+            wait_full += clock64() - t0;
+          } else {
+            ptx::mbar_wait(full_bar(stage), phase);
+          }
           ptx::tcgen05_fence_after_sync();
           const uint64_t adesc = ptx::make_smem_desc_k_sw128(smem_a0 + stage * G::A_STAGE_BYTES);
           const uint64_t bdesc = ptx::make_smem_desc_k_sw128(smem_b0 + stage * G::B_STAGE_BYTES);
@@ -240,6 +267,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+      }
+      if (dbg) {
+        dbg[blockIdx.x * 8 + 2] = wait_full;
+        dbg[blockIdx.x * 8 + 3] = wait_tmem;
+        dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
       }
     }
   } else {
@@ -335,6 +367,74 @@ transpose_prep_kernel(const T *__restrict__ src, T *__restrict__ dst, uint32_t s
   }
 }
 
+// ---- 3xTF32 operand construction (MM_FLAG_TF32X3) ------------------------------------------------
+// x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi).  A*B ~= hi_a*hi_b + hi_a*lo_b + lo_a*hi_b
+// (the dropped lo*lo term is 2^-22 relative).  The three products are folded into ONE GEMM with
+// K' = 3K by interleaving 16-element k-blocks:  A' = [hi | hi | lo],  B'^T = [hi | lo | hi],
+// so the unchanged tcgen05 kernel accumulates all three in its FP32 TMEM accumulator.
+constexpr int SPLIT_BLOCK = 16;  // K % 16 == 0 by the reference's shape rule for float
+
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+  hi = round_tf32(x);
+  lo = round_tf32(x - hi);
+}
+
+// dst[r][3K]: per 16-block of k -> [hi16 | hi16 | lo16]; one thread per float4 of the source row.
+__global__ void __launch_bounds__(256)
+split3_rows_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, size_t rows, uint32_t k) {
+  const size_t k4 = k / 4;
+  const size_t total = rows * k4;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / k4;
+    const uint32_t c4 = uint32_t(i - r * k4);       // float4 index within the row
+    const uint32_t blk = c4 / (SPLIT_BLOCK / 4), in = c4 % (SPLIT_BLOCK / 4);
+    const float4 v = src[i];
+    float4 hi, lo;
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
+    float4 *row = dst + r * (3 * k4) + size_t(blk) * (3 * SPLIT_BLOCK / 4) + in;
+    row[0] = hi;
+    row[SPLIT_BLOCK / 4] = hi;
+    row[2 * SPLIT_BLOCK / 4] = lo;
+  }
+}
+
+// src (src_rows = K) x (src_cols) row-major -> dst[c][3K] with per-16-block [a | b | c] where
+// B_ORDER selects (hi, lo, hi) for the B operand and (hi, hi, lo) for a transposed A.
+template <bool B_ORDER>
+__global__ void __launch_bounds__(256)
+split3_transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, uint32_t src_rows,
+                        uint32_t src_cols) {
+  constexpr int TILE = 64;
+  __shared__ float tile[TILE][TILE + 1];
+  const uint32_t c0 = blockIdx.x * TILE;
+  const uint32_t r0 = blockIdx.y * TILE;
+  const int x = threadIdx.x % TILE;
+  const int y = threadIdx.x / TILE;
+#pragma unroll 4
+  for (int i = y; i < TILE; i += 4) {
+    const uint32_t r = r0 + i, c = c0 + x;
+    if (r < src_rows && c < src_cols) tile[i][x] = src[size_t(r) * src_cols + c];
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int i = y; i < TILE; i += 4) {
+    const uint32_t c = c0 + i, r = r0 + x;  // dst row = src col; r = k index
+    if (c < src_cols && r < src_rows) {
+      float hi, lo;
+      split_tf32(tile[x][i], hi, lo);
+      float *out = dst + size_t(c) * (3 * size_t(src_rows)) + size_t(r / SPLIT_BLOCK) * (3 * SPLIT_BLOCK) +
+                   (r % SPLIT_BLOCK);
+      out[0] = hi;
+      out[SPLIT_BLOCK] = B_ORDER ? lo : hi;
+      out[2 * SPLIT_BLOCK] = B_ORDER ? hi : lo;
+    }
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -397,15 +497,19 @@ void launch_transpose(const void *src, void *dst, uint32_t src_rows, uint32_t sr
 
 }  // namespace
 
-size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m) {
+static bool split3(int dtype, int flags) { return dtype == MM_DTYPE_FLOAT && (flags & MM_FLAG_TF32X3); }
+
+size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m, int flags) {
   const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
-  return align_up(size_t(m) * k * eb, 1024);
+  return align_up(size_t(m) * k * eb * (split3(dtype, flags) ? 3 : 1), 1024);
 }
 
 size_t tcgen05_scratch_bytes(int dtype, unsigned n, unsigned k, unsigned m, int flags) {
   const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
-  size_t bytes = tcgen05_bt_bytes(dtype, k, m);  // B^T
-  if (dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) bytes += align_up(size_t(n) * k * eb, 1024);
+  size_t bytes = tcgen05_bt_bytes(dtype, k, m, flags);  // B^T
+  if (dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) {
+    bytes += align_up(size_t(n) * k * eb * (split3(dtype, flags) ? 3 : 1), 1024);
+  }
   return bytes;
 }
 
@@ -417,8 +521,13 @@ static bool experiment_no_round() {
 }
 
 // B (row-major K x M) -> B^T (M x K, K-major MMA operand) into `bt`; float is rounded to TF32.
-int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m, cudaStream_t stream) {
-  if (dtype == MM_DTYPE_FLOAT) {
+int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m, int flags,
+                      cudaStream_t stream) {
+  if (split3(dtype, flags)) {
+    dim3 grid((m + 63) / 64, (k + 63) / 64);
+    split3_transpose_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const float *>(b),
+                                                           static_cast<float *>(bt), k, m);
+  } else if (dtype == MM_DTYPE_FLOAT) {
     if (experiment_no_round()) {
       launch_transpose<float, false>(b, bt, k, m, stream);
     } else {
@@ -434,10 +543,23 @@ int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m
 // `rows` rows of A -> the K-major A operand.  Row-major float A is rounded into `aprep`; row-major
 // half A is used in place; A stored K x N (`transposed`, leading dimension n_total, only whole
 // matrices) is transposed into `aprep`.  *a_op receives the operand pointer.
-int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, bool transposed,
+int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, int flags,
                       const void **a_op, cudaStream_t stream) {
+  const bool transposed = (flags & MM_FLAG_TRANSPOSED_A) != 0;
   *a_op = a;
-  if (dtype == MM_DTYPE_FLOAT) {
+  if (split3(dtype, flags)) {
+    if (transposed) {
+      dim3 grid((rows + 63) / 64, (k + 63) / 64);
+      split3_transpose_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const float *>(a),
+                                                              static_cast<float *>(aprep), k, rows);
+    } else {
+      const size_t total4 = size_t(rows) * k / 4;
+      const int blocks = int(std::min<size_t>((total4 + 255) / 256, size_t(num_sms()) * 16));
+      split3_rows_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float4 *>(a),
+                                                    static_cast<float4 *>(aprep), rows, k);
+    }
+    *a_op = aprep;
+  } else if (dtype == MM_DTYPE_FLOAT) {
     if (transposed) {
       if (experiment_no_round()) {
         launch_transpose<float, false>(a, aprep, k, rows, stream);
@@ -489,14 +611,42 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // MM_TCGEN05_DEBUG=1 (diagnostics only): per-CTA stall cycle counters, printed after a sync
+  static const bool debug = std::getenv("MM_TCGEN05_DEBUG") != nullptr;
+  unsigned long long *dbg = nullptr;
+  if (debug) {
+    MM_CUDA_TRY(cudaMalloc(&dbg, sizeof(unsigned long long) * 8 * cfg.gridDim.x));
+    MM_CUDA_TRY(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 8 * cfg.gridDim.x, stream));
+  }
   MM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, static_cast<TOut *>(c), uint32_t(rows), uint32_t(m),
-                                 k_bytes));
+                                 k_bytes, dbg));
+  if (debug) {
+    MM_CUDA_TRY(cudaStreamSynchronize(stream));
+    std::vector<unsigned long long> h(8 * cfg.gridDim.x);
+    MM_CUDA_TRY(cudaMemcpy(h.data(), dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    double s[5] = {0, 0, 0, 0, 0};
+    int nlead = 0;
+    for (unsigned b = 0; b < cfg.gridDim.x; ++b) {
+      s[0] += double(h[b * 8 + 0]);
+      s[1] += double(h[b * 8 + 1]);
+      if (h[b * 8 + 4]) {
+        ++nlead;
+        s[2] += double(h[b * 8 + 2]);
+        s[3] += double(h[b * 8 + 3]);
+        s[4] += double(h[b * 8 + 4]);
+      }
+    }
+    fprintf(stderr, "[tcgen05 debug CG=%d rows=%u m=%u] producer: wait_empty %.1f%% of %.0f cyc | mma: wait_full %.1f%% wait_tmem %.1f%% of %.0f cyc\n",
+            CG, rows, m, 100.0 * s[0] / s[1], s[1] / cfg.gridDim.x, 100.0 * s[2] / s[4], 100.0 * s[3] / s[4], s[4] / nlead);
+  }
   return MM_OK;
 }
 
 // C[rows x m] = Aop[rows x k] * Bt[m x k]^T on the tensor cores.
 int tcgen05_gemm(int dtype, const void *a_op, const void *bt, void *c, unsigned rows, unsigned k,
-                 unsigned m, cudaStream_t stream) {
+                 unsigned m, int flags, cudaStream_t stream) {
+  if (split3(dtype, flags)) k *= 3;  // the operands carry [hi|hi|lo] x [hi|lo|hi] per 16-block of K
   const bool is_f32 = dtype == MM_DTYPE_FLOAT;
   const size_t eb = is_f32 ? 4 : 2;
   const int cg = cta_group_choice();
@@ -518,22 +668,20 @@ int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_b
   if (dtype != MM_DTYPE_FLOAT && dtype != MM_DTYPE_HALF) {
     return fail(MM_ERR_UNSUPPORTED, "tcgen05 path handles float and half only");
   }
-  if (g.flags & MM_FLAG_TF32X3) return fail(MM_ERR_UNSUPPORTED, "MM_FLAG_TF32X3 is not implemented yet");
-  const bool ta = (g.flags & MM_FLAG_TRANSPOSED_A) != 0;
   if (scratch_bytes < tcgen05_scratch_bytes(dtype, g.n, g.k, g.m, g.flags)) {
     return fail(MM_ERR_INVALID, "tcgen05 scratch too small");
   }
   unsigned char *sp = static_cast<unsigned char *>(scratch);
   void *bt = sp;
-  void *aprep = sp + tcgen05_bt_bytes(dtype, g.k, g.m);
+  void *aprep = sp + tcgen05_bt_bytes(dtype, g.k, g.m, g.flags);
 
-  int rc = tcgen05_prepare_b(dtype, g.b, bt, g.k, g.m, g.stream);
+  int rc = tcgen05_prepare_b(dtype, g.b, bt, g.k, g.m, g.flags, g.stream);
   if (rc != MM_OK) return rc;
   const void *a_op = nullptr;
-  rc = tcgen05_prepare_a(dtype, g.a, aprep, g.n, g.k, ta, &a_op, g.stream);
+  rc = tcgen05_prepare_a(dtype, g.a, aprep, g.n, g.k, g.flags, &a_op, g.stream);
   if (rc != MM_OK) return rc;
   if (g.ev_prep_done) MM_CUDA_TRY(cudaEventRecord(g.ev_prep_done, g.stream));
-  return tcgen05_gemm(dtype, a_op, bt, g.c, g.n, g.k, g.m, g.stream);
+  return tcgen05_gemm(dtype, a_op, bt, g.c, g.n, g.k, g.m, g.flags, g.stream);
 }
 
 }  // namespace mm

@@ -42,7 +42,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta_r
       "{\n\t"
       ".reg .b32 remote;\n\t"
       "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
       "}" ::"r"(bar), "r"(cta_rank)
       : "memory");
 }

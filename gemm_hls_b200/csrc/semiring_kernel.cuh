@@ -55,8 +55,11 @@ struct SemiringTile {
   static constexpr size_t SMEM_BYTES = 2 * (size_t(BK) * LDA + size_t(BK) * LDB) * sizeof(T);
 };
 
+// 2 CTAs (16 warps) per SM for 4-byte element types: 64 accumulators + two k-steps of fragments fit
+// in 128 registers without spilling.  8-byte types need the full 255-register budget, and 1- and
+// 2-byte types (one 32-bit register per unpacked element) spill at 128: those run 1 CTA per SM.
 template <typename T, class Map, class Reduce>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (sizeof(T) == 4) ? 2 : 1)
 semiring_tile_kernel(const T *__restrict__ A, const T *__restrict__ B, T *__restrict__ C,
                      unsigned size_n, unsigned size_k, unsigned size_m,
                      bool TRANSPOSED_A) {

@@ -66,8 +66,9 @@ enum {
    * (tcgen05 kind::f16 / kind::tf32 with FP32 accumulation in TMEM; DMMA for double), which is
    * within the reference's 1e-3 relative tolerance but not bit-identical. */
   MM_FLAG_EXACT = 2,
-  /* float (Multiply, Add) on the tensor cores with the 3xTF32 split (hi*hi + hi*lo + lo*hi):
-   * ~FP32 accuracy at 1/3 of the TF32 rate. */
+  /* float (Multiply, Add) on the tensor cores with the 3xTF32 split (hi*hi + hi*lo + lo*hi, each
+   * operand split into two TF32 values): ~FP32 accuracy (about 1e-6 relative) at 1/3 of the TF32
+   * rate.  Ignored for every other configuration. */
   MM_FLAG_TF32X3 = 4
 };
 
