@@ -124,9 +124,10 @@ template <int KIND, typename TOut, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, TOut *__restrict__ C, uint32_t rows,
-                    uint32_t cols, uint32_t k_bytes, unsigned long long *dbg) {
+                    uint32_t cols, uint32_t k_bytes, uint32_t num_stages, uint64_t l2_policy,
+                    unsigned long long *dbg) {
   using G = Geo<CG>;
-  constexpr int STAGES = G::STAGES;
+  const int STAGES = int(num_stages);  // <= G::STAGES (what the shared-memory allocation holds)
   extern __shared__ unsigned char smem_raw[];
   // 128B-swizzled tiles must start on a 1024-byte boundary (same offset in both CTAs of a pair).
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -201,17 +202,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (CG == 1) {
             ptx::mbar_arrive_expect_tx(full_bar(stage), G::STAGE_BYTES);
             ptx::tma_load_2d(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, full_bar(stage),
-                             kb * BLOCK_K_ELEMS, a_row);
+                             kb * BLOCK_K_ELEMS, a_row, l2_policy);
             ptx::tma_load_2d(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, full_bar(stage),
-                             kb * BLOCK_K_ELEMS, b_row);
+                             kb * BLOCK_K_ELEMS, b_row, l2_policy);
           } else {
             // both CTAs' bytes are accounted on the LEADER's barrier (peer bit 24 cleared)
             const uint32_t leader_bar = full_bar(stage) & 0xFEFFFFFFu;
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * G::STAGE_BYTES);
             ptx::tma_load_2d_2sm(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, leader_bar,
-                                 kb * BLOCK_K_ELEMS, a_row);
+                                 kb * BLOCK_K_ELEMS, a_row, l2_policy);
             ptx::tma_load_2d_2sm(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, leader_bar,
-                                 kb * BLOCK_K_ELEMS, b_row);
+                                 kb * BLOCK_K_ELEMS, b_row, l2_policy);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -618,8 +619,27 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
     MM_CUDA_TRY(cudaMalloc(&dbg, sizeof(unsigned long long) * 8 * cfg.gridDim.x));
     MM_CUDA_TRY(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 8 * cfg.gridDim.x, stream));
   }
+  // tuning knobs (diagnostics): ring depth and the TMA loads' L2 eviction priority
+  // Ring depth actually used (<= G::STAGES, the allocation).  Deeper rings hide more load latency
+  // but were MEASURED to multiply DRAM re-reads (ncu, float 16384^3, CTA pairs: 17.7 GB at depth 4,
+  // 32.2 GB at depth 6; half 32768^3: 69 GB vs 246 GB) and the chip is power-capped, so the
+  // sustained optimum is 5 for kind::tf32 (804 TF/s vs 762 @4, 740 @6) and 4 for kind::f16
+  // (1412 TF/s vs 1166 @5, 1113 @6) — profiles/r01_tcgen05_variants.md.
+  static const uint32_t stages = [] {
+    const char *e = std::getenv("MM_TCGEN05_STAGES");
+    const int dflt = (CG == 1) ? 4 : (KIND == ptx::KIND_TF32 ? 5 : 4);
+    const int v = e ? std::atoi(e) : dflt;
+    return uint32_t(std::min(std::max(v, 2), int(G::STAGES)));
+  }();
+  static const uint64_t l2_policy = [] {
+    const char *e = std::getenv("MM_TCGEN05_L2");
+    if (e && e[0] == 'f') return ptx::L2_EVICT_FIRST;
+    if (e && e[0] == 'n') return ptx::L2_EVICT_NORMAL;
+    if (e && e[0] == 'l') return ptx::L2_EVICT_LAST;
+    return ptx::L2_EVICT_NORMAL;
+  }();
   MM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, static_cast<TOut *>(c), uint32_t(rows), uint32_t(m),
-                                 k_bytes, dbg));
+                                 k_bytes, stages, l2_policy, dbg));
   if (debug) {
     MM_CUDA_TRY(cudaStreamSynchronize(stream));
     std::vector<unsigned long long> h(8 * cfg.gridDim.x);

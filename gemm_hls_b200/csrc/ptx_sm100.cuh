@@ -65,23 +65,28 @@ __device__ __forceinline__ void prefetch_tensormap(const void *tmap) {
 }
 // 2-D tile load global -> shared, completion signalled on `bar` (complete_tx::bytes).
 // c0 = coordinate along the contiguous (innermost) dimension, c1 = row.
+// L2 eviction-priority policies for the TMA loads (createpolicy encodings)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void *tmap, uint32_t bar,
-                                            int32_t c0, int32_t c1) {
+                                            int32_t c0, int32_t c1, uint64_t l2_policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(l2_policy)
       : "memory");
 }
 // Same, issued from either CTA of a cta_group::2 pair: data lands in the ISSUING CTA's shared
 // memory, the transaction bytes are signalled on the barrier at `bar`'s offset in the LEADER CTA
 // (the caller passes the leader-mapped barrier address).
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const void *tmap, uint32_t bar,
-                                                int32_t c0, int32_t c1) {
+                                                int32_t c0, int32_t c1, uint64_t l2_policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(l2_policy)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t smem_src, int32_t c0,

@@ -122,6 +122,21 @@ def test_half_small_k_against_half_accumulating_oracle(mm, oracle):
     assert max_rel(c, ref) < 1e-2
 
 
+@pytest.mark.parametrize("n,k,m,flags", [(512, 1024, 512, 4), (129, 48, 272, 4), (130, 64, 192, 4 | 1)])
+def test_float_tf32x3(mm, oracle, n, k, m, flags):
+    """MM_FLAG_TF32X3: 3xTF32 split on the tensor cores.  The operand error drops to 2^-22, what
+    remains is the tensor core's truncating FP32 accumulation (about K/8 * 3 * 2^-25 relative, biased):
+    1.3e-5 observed at K = 1024 against an FP64 evaluation, vs 6e-5 for the single-pass path.
+    Tolerance 3e-5."""
+    a, b = oracle.fill(oracle.FLOAT, n, k, m)
+    c = mm.matrix_multiplication_kernel(a, b, n, k, m, dtype=mm.FLOAT, flags=flags)
+    a2 = a.reshape(k, n).T if flags & 1 else a.reshape(n, k)
+    exact = a2.astype(np.float64) @ b.reshape(k, m).astype(np.float64)
+    assert max_rel(c, exact) <= 3e-5
+    ref = oracle.naive(oracle.FLOAT, oracle.MULTIPLY, oracle.ADD, a, b, n, k, m, transposed_a=bool(flags & 1), threads=8)
+    assert oracle.verify(oracle.FLOAT, c, ref) == -1
+
+
 def test_tf32_unbiased(mm, oracle):
     """Round-to-nearest operand preparation keeps the error centred: the MEAN signed relative
     error over C must be far below the 2^-11 a truncating feed would show."""
