@@ -67,12 +67,12 @@ struct TileCoord {
 
 // Grouped rasterisation: RASTER_GROUP row-tiles sweep all column-tiles together so that the
 // concurrently running tiles share A row-panels and B column-panels through L2.
-template <int RASTER_GROUP>
-__device__ __forceinline__ TileCoord tile_coord(uint32_t t, uint32_t tiles_r, uint32_t tiles_c) {
-  const uint32_t per_group = RASTER_GROUP * tiles_c;
+__device__ __forceinline__ TileCoord tile_coord(uint32_t t, uint32_t tiles_r, uint32_t tiles_c,
+                                                uint32_t raster_group) {
+  const uint32_t per_group = raster_group * tiles_c;
   const uint32_t g = t / per_group;
-  const uint32_t first = g * RASTER_GROUP;
-  const uint32_t gsize = min(static_cast<uint32_t>(RASTER_GROUP), tiles_r - first);
+  const uint32_t first = g * raster_group;
+  const uint32_t gsize = min(raster_group, tiles_r - first);
   const uint32_t in = t - g * per_group;
   return TileCoord{first + in % gsize, in / gsize};
 }
@@ -124,8 +124,8 @@ template <int KIND, typename TOut, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, TOut *__restrict__ C, uint32_t rows,
-                    uint32_t cols, uint32_t k_bytes, uint32_t num_stages, uint64_t l2_policy,
-                    unsigned long long *dbg) {
+                    uint32_t cols, uint32_t k_bytes, uint32_t num_stages, uint32_t raster_group,
+                    uint64_t l2_policy, unsigned long long *dbg) {
   using G = Geo<CG>;
   const int STAGES = int(num_stages);  // <= G::STAGES (what the shared-memory allocation holds)
   extern __shared__ unsigned char smem_raw[];
@@ -188,7 +188,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t stage = 0, phase = 0;
       long long wait_empty = 0, t_begin = clock64();
       for (uint32_t t = group_id; t < num_tiles; t += num_groups) {
-        const TileCoord tc = tile_coord<G::RASTER_GROUP>(t, tiles_r, tiles_c);
+        const TileCoord tc = tile_coord(t, tiles_r, tiles_c, raster_group);
         const int32_t a_row = tc.r * G::TILE_ROWS + cta_rank * BLOCK_M;
         const int32_t b_row = tc.c * BLOCK_N + cta_rank * G::LOAD_N;
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
@@ -280,7 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, +32) are this warp's
     uint32_t iter = 0;
     for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++iter) {
-      const TileCoord tc = tile_coord<G::RASTER_GROUP>(t, tiles_r, tiles_c);
+      const TileCoord tc = tile_coord(t, tiles_r, tiles_c, raster_group);
       const uint32_t as = iter & 1u;
       const uint32_t aphase = (iter >> 1) & 1u;
       ptx::mbar_wait(tmem_full_bar(as), aphase);
@@ -638,8 +638,15 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
     if (e && e[0] == 'l') return ptx::L2_EVICT_LAST;
     return ptx::L2_EVICT_NORMAL;
   }();
+  // rows of C per rasterisation group = the height of the patch that co-running tiles share
+  // through L2 (the "memory tile" of the reference's I/O model); scripts/tile_sweep.py sweeps it
+  static const uint32_t raster_group = [] {
+    const char *e = std::getenv("MM_TCGEN05_RASTER_ROWS");
+    const int rows_per_group = e ? std::atoi(e) : RASTER_GROUP_ROWS;
+    return uint32_t(std::max(1, rows_per_group / G::TILE_ROWS));
+  }();
   MM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, static_cast<TOut *>(c), uint32_t(rows), uint32_t(m),
-                                 k_bytes, stages, l2_policy, dbg));
+                                 k_bytes, stages, raster_group, l2_policy, dbg));
   if (debug) {
     MM_CUDA_TRY(cudaStreamSynchronize(stream));
     std::vector<unsigned long long> h(8 * cfg.gridDim.x);

@@ -15,6 +15,9 @@
 #include "Device.h"
 #include "MatrixMultiplication.h"
 #include "Utility.h"
+#ifdef MM_HAS_NCCL
+#include "MultiGpu.h"
+#endif
 
 void PrintUsage() {
 #ifndef MM_DYNAMIC_SIZES
@@ -90,6 +93,41 @@ int main(int argc, char **argv) {
   }
   std::cout << " Done.\n";
 
+  // MM_NUM_GPUS=G (G > 1): split C row-blocks over G GPUs of this box, B broadcast once over NCCL
+  // (SURVEY.md section 8e).  Same stdout contract; the reported time is the slowest GPU's kernel time.
+  const char *gpus_env = std::getenv("MM_NUM_GPUS");
+  const int num_gpus = gpus_env ? std::atoi(gpus_env) : 1;
+  if (num_gpus > 1) {
+#ifdef MM_HAS_NCCL
+    try {
+      std::cout << "Initializing " << num_gpus << " CUDA contexts and NCCL...\n" << std::flush;
+      mm::MultiGpuRun run(num_gpus, kDataTypeCode, kMapOpCode, kReduceOpCode, kKernelFlags, size_n, size_k,
+                          size_m, sizeof(Data_t));
+      if (verify) {
+        std::cout << "Copying memory to device...\n" << std::flush;
+        run.CopyFromHost(a.data(), b.data());
+      }
+      std::cout << "Broadcasting B over NCCL...\n" << std::flush;
+      const double bcast = run.BroadcastB();
+      std::cout << "Executing kernel...\n" << std::flush;
+      const auto elapsed = run.Execute();
+      const auto perf = 1e-9 * (2 * static_cast<float>(size_n) * size_k * size_m) / elapsed.first;
+      std::cout << "Kernel executed in " << elapsed.first << " seconds, corresponding to a performance of " << perf
+                << " GOp/s.\n";
+      std::cout << "NCCL broadcast of B took " << bcast << " seconds on " << num_gpus << " GPUs.\n";
+      if (verify) {
+        std::cout << "Copying back result...\n" << std::flush;
+        run.CopyToHost(cMem.data());
+      }
+    } catch (std::runtime_error const &err) {
+      std::cerr << "Execution failed with error: \"" << err.what() << "\"." << std::endl;
+      return 1;
+    }
+#else
+    std::cerr << "Execution failed with error: \"MM_NUM_GPUS > 1 needs a build with NCCL (MM_HAS_NCCL)\"." << std::endl;
+    return 1;
+#endif
+  } else
   try {
     std::cout << "Initializing CUDA context...\n" << std::flush;
     const char *dev_env = std::getenv("MM_DEVICE");

@@ -25,15 +25,20 @@ KEYS = ['Kernel Name', 'launch__grid_size', 'launch__block_size', 'launch__regis
         'smsp__pcsamp_warps_issue_stalled_barrier', 'smsp__pcsamp_warps_issue_stalled_not_selected',
         'smsp__pcsamp_warps_issue_stalled_dispatch_stall', 'smsp__pcsamp_warps_issue_stalled_wait',
         'smsp__pcsamp_warps_issue_stalled_lg_throttle', 'smsp__pcsamp_warps_issue_stalled_selected']
-for path in sys.argv[1:]:
-    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    hdr, units = rows[0], rows[1]
-    print('=== ' + path)
-    for r in rows[2:]:
-        d = dict(zip(hdr, r))
-        for k in KEYS:
-            if k in d:
-                name = d[k] if k != 'Kernel Name' else d[k][:110]
-                print('  %-82s %s %s' % (k, name, units[hdr.index(k)]))
-        print('  --')
+def main(paths):
+  for path in paths:
+      out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+      rows = list(csv.reader(out.splitlines()))
+      hdr, units = rows[0], rows[1]
+      print('=== ' + path)
+      for r in rows[2:]:
+          d = dict(zip(hdr, r))
+          for k in KEYS:
+              if k in d:
+                  name = d[k] if k != 'Kernel Name' else d[k][:110]
+                  print('  %-82s %s %s' % (k, name, units[hdr.index(k)]))
+          print('  --')
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:])
