@@ -308,8 +308,9 @@ int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags) {
   if (!valid_dtype(dtype) || !valid_op(map_op) || !valid_op(reduce_op)) return -1;
   switch (select_path(dtype, map_op, reduce_op, flags)) {
     case kPathTcgen05:
-      // B^T prep + (A prep for float or transposed A) + GEMM
-      return (dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) ? 3 : 2;
+      // [B^T prep unless B is read directly] + [A prep for float or transposed A] + GEMM
+      return 1 + (mm::tcgen05_b_direct(dtype) ? 0 : 1) +
+             ((dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) ? 1 : 0);
     case kPathDmma: return 1;
     case kPathSemiring: return 1;
   }
@@ -401,8 +402,9 @@ int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flag
   }
   MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev_b, 0));
   MM_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
+  const void *b_op = nullptr;
   if (path == kPathTcgen05) {
-    if ((rc = mm::tcgen05_prepare_b(dtype, db, bt, k, m, flags, ctx->stream)) != MM_OK) return rc;
+    if ((rc = mm::tcgen05_prepare_b(dtype, db, bt, k, m, flags, &b_op, ctx->stream)) != MM_OK) return rc;
   }
   for (unsigned i = 0; i < chunks; ++i) {
     const size_t r0 = size_t(i) * chunk_rows, rows = std::min<size_t>(chunk_rows, n - r0);
@@ -415,7 +417,9 @@ int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flag
       rc = mm::tcgen05_prepare_a(dtype, a_chunk, aprep + (ta ? 0 : r0 * k * es * a_scale), unsigned(rows), k, flags,
                                  &a_op, ctx->stream);
       if (rc != MM_OK) return rc;
-      rc = mm::tcgen05_gemm(dtype, a_op, bt, c_chunk, unsigned(rows), k, m, flags, ctx->stream);
+      unsigned int *tile_sync = reinterpret_cast<unsigned int *>(
+          static_cast<unsigned char *>(ctx->scratch.ptr) + ctx->scratch.bytes - 256);
+      rc = mm::tcgen05_gemm(dtype, a_op, b_op, c_chunk, unsigned(rows), k, m, flags, tile_sync, ctx->stream);
     } else {
       mm::GemmArgs g{a_chunk, db, c_chunk, unsigned(rows), k, m, flags, ctx->stream};
       rc = (path == kPathDmma) ? mm::launch_dmma(g) : mm::launch_semiring(dtype, map_op, reduce_op, g);

@@ -55,12 +55,16 @@ size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m, int flags);  // offse
 int launch_tcgen05(int dtype, const GemmArgs &args, void *scratch, size_t scratch_bytes);
 // The three phases of launch_tcgen05, for callers that reuse a prepared B across row-blocks
 // (the pipelined host path, multi-GPU row-block drivers):
+// *b_op receives the B operand of tcgen05_gemm: `bt` (prepared K-major copy) or `b` itself when the
+// kernel reads the row-major B directly (half).
 int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m, int flags,
-                      cudaStream_t stream);
+                      const void **b_op, cudaStream_t stream);
+bool tcgen05_b_direct(int dtype);
 int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, int flags,
                       const void **a_op, cudaStream_t stream);
-int tcgen05_gemm(int dtype, const void *a_op, const void *bt, void *c, unsigned rows, unsigned k,
-                 unsigned m, int flags, cudaStream_t stream);
+// `tile_sync`: device counter (zeroed by the launcher) for the kernel's soft wave barrier, or null.
+int tcgen05_gemm(int dtype, const void *a_op, const void *b_op, void *c, unsigned rows, unsigned k,
+                 unsigned m, int flags, unsigned int *tile_sync, cudaStream_t stream);
 
 // DMMA (mma.sync m8n8k4 f64) GEMM for (Multiply, Add) double.  gemm_dmma.cu
 int launch_dmma(const GemmArgs &args);

@@ -42,6 +42,8 @@ constexpr int UMMA_K_BYTES = 32;      // K extent of one tcgen05.mma
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
 constexpr int NUM_THREADS = 192;
+constexpr int MN_ATOM = 64;                       // elements of N per MN-major swizzle atom (128 B of f16)
+constexpr int MN_ATOM_BYTES = 64 * BLOCK_K_BYTES; // one atom: BLOCK_K (= 64 for f16) k-rows x 128 B
 constexpr int RASTER_GROUP_ROWS = 2048;  // C rows per rasterisation group (L2 reuse of B^T panels)
 
 // Per-variant geometry.  CG = 1: one CTA computes a 128 x 256 tile and stages A (128 rows) + B^T
@@ -120,12 +122,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 // C[rows x cols] = A'[rows x k] * Bt[cols x k]^T ; A', Bt K-major, described by the tensor maps.
 // CG == 2 must be launched with cluster dimension (2, 1, 1).
-template <int KIND, typename TOut, int CG>
+// BMN: the B operand is read MN-major straight from the reference's row-major B (K x M) — no
+// transposed copy.  Implemented for kind::f16 (64-element atoms); kind::tf32 needs B rounded to
+// TF32 anyway, so its prepared copy is written K-major.
+template <int KIND, typename TOut, int CG, bool BMN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, TOut *__restrict__ C, uint32_t rows,
                     uint32_t cols, uint32_t k_bytes, uint32_t num_stages, uint32_t raster_group,
-                    uint64_t l2_policy, unsigned long long *dbg) {
+                    uint64_t l2_policy, unsigned int *tile_sync, unsigned long long *dbg) {
   using G = Geo<CG>;
   const int STAGES = int(num_stages);  // <= G::STAGES (what the shared-memory allocation holds)
   extern __shared__ unsigned char smem_raw[];
@@ -187,7 +192,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       long long wait_empty = 0, t_begin = clock64();
-      for (uint32_t t = group_id; t < num_tiles; t += num_groups) {
+      uint32_t tile_iter = 0;
+      for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++tile_iter) {
+        // Soft wave barrier: do not start fetching tile #j before every CTA group has finished
+        // fetching its tile #(j-1).  A ring deep enough to hide DRAM latency removes the L2-miss
+        // back-pressure that otherwise keeps the co-running tiles in lock-step, the groups drift,
+        // and the A / B^T panels they share are re-read from DRAM (measured: 17.7 -> 32 GB at
+        // 16384^3).  Purely a performance hint: the wait is bounded, correctness never depends on it.
+        if (tile_sync != nullptr && tile_iter > 0) {
+          const uint32_t target = min(tile_iter * num_groups, num_tiles);
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile unsigned int *>(tile_sync) < target) {
+            if (clock64() - t0 > 100000) break;  // ~50 us: give up, stay correct
+          }
+        }
         const TileCoord tc = tile_coord(t, tiles_r, tiles_c, raster_group);
         const int32_t a_row = tc.r * G::TILE_ROWS + cta_rank * BLOCK_M;
         const int32_t b_row = tc.c * BLOCK_N + cta_rank * G::LOAD_N;
@@ -203,19 +221,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             ptx::mbar_arrive_expect_tx(full_bar(stage), G::STAGE_BYTES);
             ptx::tma_load_2d(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, full_bar(stage),
                              kb * BLOCK_K_ELEMS, a_row, l2_policy);
-            ptx::tma_load_2d(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, full_bar(stage),
-                             kb * BLOCK_K_ELEMS, b_row, l2_policy);
+            if (BMN) {
+#pragma unroll
+              for (int j = 0; j < G::LOAD_N / MN_ATOM; ++j) {
+                ptx::tma_load_2d(smem_b0 + stage * G::B_STAGE_BYTES + j * MN_ATOM_BYTES, &tmap_b, full_bar(stage),
+                                 b_row + j * MN_ATOM, kb * BLOCK_K_ELEMS, l2_policy);
+              }
+            } else {
+              ptx::tma_load_2d(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, full_bar(stage),
+                               kb * BLOCK_K_ELEMS, b_row, l2_policy);
+            }
           } else {
             // both CTAs' bytes are accounted on the LEADER's barrier (peer bit 24 cleared)
             const uint32_t leader_bar = full_bar(stage) & 0xFEFFFFFFu;
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * G::STAGE_BYTES);
             ptx::tma_load_2d_2sm(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, leader_bar,
                                  kb * BLOCK_K_ELEMS, a_row, l2_policy);
-            ptx::tma_load_2d_2sm(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, leader_bar,
-                                 kb * BLOCK_K_ELEMS, b_row, l2_policy);
+            if (BMN) {
+#pragma unroll
+              for (int j = 0; j < G::LOAD_N / MN_ATOM; ++j) {
+                ptx::tma_load_2d_2sm(smem_b0 + stage * G::B_STAGE_BYTES + j * MN_ATOM_BYTES, &tmap_b, leader_bar,
+                                     b_row + j * MN_ATOM, kb * BLOCK_K_ELEMS, l2_policy);
+              }
+            } else {
+              ptx::tma_load_2d_2sm(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, leader_bar,
+                                   kb * BLOCK_K_ELEMS, b_row, l2_policy);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (tile_sync != nullptr && cta_rank == 0) atomicAdd(tile_sync, 1u);  // this group fetched its tile
       }
       if (dbg) {
         dbg[blockIdx.x * 8 + 0] = wait_empty;
@@ -225,7 +260,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc(KIND, BLOCK_M * CG, BLOCK_N);
+      constexpr uint32_t idesc = ptx::make_idesc(KIND, BLOCK_M * CG, BLOCK_N, BMN);
       uint32_t stage = 0, phase = 0, iter = 0;
       long long wait_full = 0, wait_tmem = 0, t_begin = clock64();
       for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++iter) {
@@ -250,13 +285,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           ptx::tcgen05_fence_after_sync();
           const uint64_t adesc = ptx::make_smem_desc_k_sw128(smem_a0 + stage * G::A_STAGE_BYTES);
-          const uint64_t bdesc = ptx::make_smem_desc_k_sw128(smem_b0 + stage * G::B_STAGE_BYTES);
+          const uint64_t bdesc = BMN ? ptx::make_smem_desc_mn_sw128(smem_b0 + stage * G::B_STAGE_BYTES, MN_ATOM_BYTES)
+                                     : ptx::make_smem_desc_k_sw128(smem_b0 + stage * G::B_STAGE_BYTES);
+          // K-major: advancing K inside the swizzle atom = advancing the start address by 32 B;
+          // MN-major: one UMMA_K is UMMA_K_ELEMS k-rows of 128 B.
+          constexpr uint32_t UMMA_K_ELEMS = UMMA_K_BYTES / ELEM_BYTES;
+          constexpr uint32_t b_step = BMN ? (UMMA_K_ELEMS * 128u) >> 4 : uint32_t(UMMA_K_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K_BYTES / UMMA_K_BYTES; ++k) {
-            // advancing K inside the swizzle atom = advancing the start address (>>4 units)
-            ptx::umma<KIND, CG>(tmem_d, adesc + uint64_t(k * (UMMA_K_BYTES >> 4)),
-                                bdesc + uint64_t(k * (UMMA_K_BYTES >> 4)), idesc,
-                                (kb | uint32_t(k)) != 0u ? 1u : 0u);
+            ptx::umma<KIND, CG>(tmem_d, adesc + uint64_t(k * (UMMA_K_BYTES >> 4)), bdesc + uint64_t(k * b_step),
+                                idesc, (kb | uint32_t(k)) != 0u ? 1u : 0u);
           }
           // smem stage reusable / accumulator complete once these MMAs retire
           if (CG == 1) {
@@ -479,6 +517,23 @@ int make_operand_map(CUtensorMap *map, const void *base, int dtype, uint64_t row
   return MM_OK;
 }
 
+// MN-major B operand read from row-major B (K x M): box = {64 elements of M (128 B), 64 k-rows}.
+int make_b_mn_map(CUtensorMap *map, const void *base, uint64_t k, uint64_t m) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {m, k};
+  cuuint64_t gstride[1] = {m * 2};
+  cuuint32_t box[2] = {uint32_t(MN_ATOM), uint32_t(BLOCK_K_BYTES / 2)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled (MN-major B) failed with CUresult " + std::to_string(int(r)));
+  }
+  return MM_OK;
+}
+
 int num_sms() {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -498,16 +553,29 @@ void launch_transpose(const void *src, void *dst, uint32_t src_rows, uint32_t sr
 
 }  // namespace
 
+constexpr size_t TILE_SYNC_BYTES = 256;  // the soft wave-barrier counter lives in the LAST 256 bytes of the scratch
+
 static bool split3(int dtype, int flags) { return dtype == MM_DTYPE_FLOAT && (flags & MM_FLAG_TF32X3); }
 
+// half: B is consumed MN-major straight from the caller's row-major K x M array (no B^T copy).
+// MM_TCGEN05_B_MN=0 restores the transposed-copy path for A/B measurements.
+bool tcgen05_b_direct(int dtype) {
+  static const bool enabled = [] {
+    const char *e = std::getenv("MM_TCGEN05_B_MN");
+    return !(e && e[0] == '0');
+  }();
+  return dtype == MM_DTYPE_HALF && enabled;
+}
+
 size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m, int flags) {
+  if (tcgen05_b_direct(dtype)) return 0;
   const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
   return align_up(size_t(m) * k * eb * (split3(dtype, flags) ? 3 : 1), 1024);
 }
 
 size_t tcgen05_scratch_bytes(int dtype, unsigned n, unsigned k, unsigned m, int flags) {
   const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
-  size_t bytes = tcgen05_bt_bytes(dtype, k, m, flags);  // B^T
+  size_t bytes = TILE_SYNC_BYTES + tcgen05_bt_bytes(dtype, k, m, flags);  // wave-barrier counter (tail) + B^T
   if (dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) {
     bytes += align_up(size_t(n) * k * eb * (split3(dtype, flags) ? 3 : 1), 1024);
   }
@@ -523,7 +591,12 @@ static bool experiment_no_round() {
 
 // B (row-major K x M) -> B^T (M x K, K-major MMA operand) into `bt`; float is rounded to TF32.
 int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m, int flags,
-                      cudaStream_t stream) {
+                      const void **b_op, cudaStream_t stream) {
+  *b_op = bt;
+  if (tcgen05_b_direct(dtype)) {
+    *b_op = b;  // nothing to prepare
+    return MM_OK;
+  }
   if (split3(dtype, flags)) {
     dim3 grid((m + 63) / 64, (k + 63) / 64);
     split3_transpose_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const float *>(b),
@@ -592,11 +665,11 @@ static int cta_group_choice() {
   return v;
 }
 
-template <int KIND, typename TOut, int CG>
+template <int KIND, typename TOut, int CG, bool BMN>
 static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_b, void *c, unsigned rows,
-                               unsigned m, uint32_t k_bytes, cudaStream_t stream) {
+                               unsigned m, uint32_t k_bytes, unsigned int *tile_sync, cudaStream_t stream) {
   using G = Geo<CG>;
-  auto kern = gemm_tcgen05_kernel<KIND, TOut, CG>;
+  auto kern = gemm_tcgen05_kernel<KIND, TOut, CG, BMN>;
   MM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G::SMEM_BYTES)));
   const uint32_t tiles = ceil_div(rows, G::TILE_ROWS) * ceil_div(m, BLOCK_N);
   const uint32_t groups = std::min<uint32_t>(tiles, uint32_t(num_sms()) / CG);
@@ -620,14 +693,14 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
     MM_CUDA_TRY(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 8 * cfg.gridDim.x, stream));
   }
   // tuning knobs (diagnostics): ring depth and the TMA loads' L2 eviction priority
-  // Ring depth actually used (<= G::STAGES, the allocation).  Deeper rings hide more load latency
-  // but were MEASURED to multiply DRAM re-reads (ncu, float 16384^3, CTA pairs: 17.7 GB at depth 4,
-  // 32.2 GB at depth 6; half 32768^3: 69 GB vs 246 GB) and the chip is power-capped, so the
-  // sustained optimum is 5 for kind::tf32 (804 TF/s vs 762 @4, 740 @6) and 4 for kind::f16
-  // (1412 TF/s vs 1166 @5, 1113 @6) — profiles/r01_tcgen05_variants.md.
+  // Ring depth actually used (<= G::STAGES, the allocation).  Measured (profiles/exp_tile_sync.log,
+  // float 16384^3 / half 32768^3, CTA pairs, WITH the soft wave barrier): depth 4 leaves the tensor
+  // pipe 79-86 % active, depth 5-6 reach 96-98 % at unchanged DRAM traffic (17.7 / 68.8 GB).  Without
+  // the barrier depth >= 5 multiplied the DRAM re-reads (27.6 / 31.7 GB at depth 5 / 6, 246 GB for
+  // half at depth 6) and lowered the sustained, power-capped rate.
   static const uint32_t stages = [] {
     const char *e = std::getenv("MM_TCGEN05_STAGES");
-    const int dflt = (CG == 1) ? 4 : (KIND == ptx::KIND_TF32 ? 5 : 4);
+    const int dflt = G::STAGES;
     const int v = e ? std::atoi(e) : dflt;
     return uint32_t(std::min(std::max(v, 2), int(G::STAGES)));
   }();
@@ -645,8 +718,14 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
     const int rows_per_group = e ? std::atoi(e) : RASTER_GROUP_ROWS;
     return uint32_t(std::max(1, rows_per_group / G::TILE_ROWS));
   }();
+  static const bool use_tile_sync = [] {
+    const char *e = std::getenv("MM_TCGEN05_TILE_SYNC");
+    return !(e && e[0] == '0');
+  }();
+  if (!use_tile_sync) tile_sync = nullptr;
+  if (tile_sync) MM_CUDA_TRY(cudaMemsetAsync(tile_sync, 0, sizeof(unsigned int), stream));
   MM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, static_cast<TOut *>(c), uint32_t(rows), uint32_t(m),
-                                 k_bytes, stages, raster_group, l2_policy, dbg));
+                                 k_bytes, stages, raster_group, l2_policy, tile_sync, dbg));
   if (debug) {
     MM_CUDA_TRY(cudaStreamSynchronize(stream));
     std::vector<unsigned long long> h(8 * cfg.gridDim.x);
@@ -670,25 +749,32 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
   return MM_OK;
 }
 
-// C[rows x m] = Aop[rows x k] * Bt[m x k]^T on the tensor cores.
-int tcgen05_gemm(int dtype, const void *a_op, const void *bt, void *c, unsigned rows, unsigned k,
-                 unsigned m, int flags, cudaStream_t stream) {
+// C[rows x m] = Aop[rows x k] * B on the tensor cores; `b_op` is the K-major copy B^T (m x k), or
+// the caller's row-major B (k x m) when tcgen05_b_direct(dtype).
+int tcgen05_gemm(int dtype, const void *a_op, const void *b_op, void *c, unsigned rows, unsigned k,
+                 unsigned m, int flags, unsigned int *tile_sync, cudaStream_t stream) {
   if (split3(dtype, flags)) k *= 3;  // the operands carry [hi|hi|lo] x [hi|lo|hi] per 16-block of K
   const bool is_f32 = dtype == MM_DTYPE_FLOAT;
   const size_t eb = is_f32 ? 4 : 2;
   const int cg = cta_group_choice();
+  const bool bmn = tcgen05_b_direct(dtype);
   CUtensorMap map_a, map_b;
   int rc = make_operand_map(&map_a, a_op, dtype, rows, k, BLOCK_M);
   if (rc != MM_OK) return rc;
-  rc = make_operand_map(&map_b, bt, dtype, m, k, cg == 2 ? Geo<2>::LOAD_N : Geo<1>::LOAD_N);
+  rc = bmn ? make_b_mn_map(&map_b, b_op, k, m)
+           : make_operand_map(&map_b, b_op, dtype, m, k, cg == 2 ? Geo<2>::LOAD_N : Geo<1>::LOAD_N);
   if (rc != MM_OK) return rc;
   const uint32_t k_bytes = uint32_t(size_t(k) * eb);
   if (is_f32) {
-    return cg == 2 ? launch_gemm_variant<ptx::KIND_TF32, float, 2>(map_a, map_b, c, rows, m, k_bytes, stream)
-                   : launch_gemm_variant<ptx::KIND_TF32, float, 1>(map_a, map_b, c, rows, m, k_bytes, stream);
+    return cg == 2 ? launch_gemm_variant<ptx::KIND_TF32, float, 2, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream)
+                   : launch_gemm_variant<ptx::KIND_TF32, float, 1, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream);
   }
-  return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2>(map_a, map_b, c, rows, m, k_bytes, stream)
-                 : launch_gemm_variant<ptx::KIND_F16, __half, 1>(map_a, map_b, c, rows, m, k_bytes, stream);
+  if (bmn) {
+    return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream)
+                   : launch_gemm_variant<ptx::KIND_F16, __half, 1, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream);
+  }
+  return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream)
+                 : launch_gemm_variant<ptx::KIND_F16, __half, 1, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream);
 }
 
 int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_bytes) {
@@ -701,14 +787,16 @@ int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_b
   unsigned char *sp = static_cast<unsigned char *>(scratch);
   void *bt = sp;
   void *aprep = sp + tcgen05_bt_bytes(dtype, g.k, g.m, g.flags);
+  unsigned int *tile_sync = reinterpret_cast<unsigned int *>(sp + scratch_bytes - TILE_SYNC_BYTES);
 
-  int rc = tcgen05_prepare_b(dtype, g.b, bt, g.k, g.m, g.flags, g.stream);
+  const void *b_op = nullptr;
+  int rc = tcgen05_prepare_b(dtype, g.b, bt, g.k, g.m, g.flags, &b_op, g.stream);
   if (rc != MM_OK) return rc;
   const void *a_op = nullptr;
   rc = tcgen05_prepare_a(dtype, g.a, aprep, g.n, g.k, g.flags, &a_op, g.stream);
   if (rc != MM_OK) return rc;
   if (g.ev_prep_done) MM_CUDA_TRY(cudaEventRecord(g.ev_prep_done, g.stream));
-  return tcgen05_gemm(dtype, a_op, bt, g.c, g.n, g.k, g.m, g.flags, g.stream);
+  return tcgen05_gemm(dtype, a_op, b_op, g.c, g.n, g.k, g.m, g.flags, tile_sync, g.stream);
 }
 
 }  // namespace mm

@@ -226,13 +226,28 @@ __device__ __forceinline__ uint64_t make_smem_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (element (mn, k) at mn contiguous): stored as 64-element (128-byte) wide atoms of
+// `k` rows x 128 B with the 128-byte swizzle — what a TMA box {64 elements of MN, k rows} writes.
+// Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = byte distance between
+// consecutive 64-element MN atoms, SBO = 1024 B between groups of 8 k-rows.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor (upper 32 bits of the 64-bit idesc operand), dense, FP32 accumulate,
 // both operands K-major:
 //   [4,6) D format (1 = F32)   [7,10) A format   [10,13) B format  (0 = F16, 1 = BF16, 2 = TF32)
-//   [15] A major (0 = K)  [16] B major (0 = K)   [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc(int kind, uint32_t umma_m, uint32_t umma_n) {
+//   [15] A major (0 = K)  [16] B major (0 = K, 1 = MN)   [17,23) N >> 3   [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(int kind, uint32_t umma_m, uint32_t umma_n,
+                                                  bool b_mn_major = false) {
   return (1u << 4) | ((kind == KIND_TF32 ? 2u : 0u) << 7) | ((kind == KIND_TF32 ? 2u : 0u) << 10) |
-         ((umma_n >> 3) << 17) | ((umma_m >> 4) << 24);
+         ((b_mn_major ? 1u : 0u) << 16) | ((umma_n >> 3) << 17) | ((umma_m >> 4) << 24);
 }
 
 }  // namespace ptx
