@@ -42,6 +42,10 @@ struct GemmArgs {
   // and the main kernel when non-null
   cudaEvent_t ev_start = nullptr;
   cudaEvent_t ev_prep_done = nullptr;
+  // Resource-preparation pass: do everything a launch does EXCEPT enqueue kernels (set function
+  // attributes, which also forces the lazily loaded cubin in).  mm_kernel_execute runs it before
+  // recording its start event so that the reported device time is kernel time only.
+  bool dry_run = false;
 };
 
 // ---- kernel families (one launcher per translation unit) ---------------------------------------

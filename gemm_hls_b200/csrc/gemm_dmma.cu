@@ -162,6 +162,7 @@ int launch_dmma(const GemmArgs &g) {
   if (ta && (g.n % 2 != 0)) return fail(MM_ERR_UNSUPPORTED, "dmma path with transposed A needs even N");
   MM_CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
   MM_CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+  if (g.dry_run) return MM_OK;
   dim3 grid(ceil_div(g.m, BN), ceil_div(g.n, BM));
   const double *a = static_cast<const double *>(g.a);
   const double *b = static_cast<const double *>(g.b);

@@ -784,6 +784,17 @@ int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_b
   if (scratch_bytes < tcgen05_scratch_bytes(dtype, g.n, g.k, g.m, g.flags)) {
     return fail(MM_ERR_INVALID, "tcgen05 scratch too small");
   }
+  if (g.dry_run) {
+    // force the lazily loaded kernels in (prep + GEMM variants) and the driver entry point
+    cudaFuncAttributes attr;
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, round_tf32_kernel));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, transpose_prep_kernel<float, true>));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, transpose_prep_kernel<__half, false>));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_TF32, float, 2, false>));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_F16, __half, 2, true>));
+    if (!get_encode_fn()) return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    return MM_OK;
+  }
   unsigned char *sp = static_cast<unsigned char *>(scratch);
   void *bt = sp;
   void *aprep = sp + tcgen05_bt_bytes(dtype, g.k, g.m, g.flags);

@@ -29,7 +29,9 @@ int by_map_float(int map_op, int reduce_op, const GemmArgs &g, bool ta) {
 
 }  // namespace
 
-int launch_semiring(int dtype, int map_op, int reduce_op, const GemmArgs &g) {
+int launch_semiring(int dtype, int map_op, int reduce_op, const GemmArgs &g_in) {
+  GemmArgs g = g_in;
+  if (g.dry_run) g.a = nullptr;  // launch_semiring_typed: null A = load the kernel, launch nothing
   const bool ta = (g.flags & MM_FLAG_TRANSPOSED_A) != 0;
   int rc = -1;
   switch (dtype) {

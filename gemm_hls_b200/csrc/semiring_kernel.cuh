@@ -211,6 +211,10 @@ template <typename T, class Map, class Reduce>
 int launch_semiring_typed(const void *a, const void *b, void *c, unsigned n, unsigned k, unsigned m,
                           bool transposed_a, cudaStream_t stream) {
   using Cfg = SemiringTile<T>;
+  if (a == nullptr) {  // dry run: only make sure the kernel is loaded
+    cudaFuncAttributes attr;
+    return static_cast<int>(cudaFuncGetAttributes(&attr, semiring_tile_kernel<T, Map, Reduce>));
+  }
   dim3 grid((m + Cfg::BN - 1) / Cfg::BN, (n + Cfg::BM - 1) / Cfg::BM);
   dim3 block(Cfg::THREADS);
   const T *pa = static_cast<const T *>(a);
