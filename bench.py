@@ -292,9 +292,12 @@ def main():
             peak_note = "nominal FP64 tensor (DMMA) 37 TF/s per GPU (datasheet; not in MEASURED_PEAKS.json)"
             roof = {"bound": "tensor", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TFLOP/s"}
         else:
-            peak = 36.0  # derived CUDA-core ceiling for (add, min): see DESIGN.md
-            peak_note = "derived FP32 add+min issue ceiling 36 TOp/s (DESIGN.md); kernel is not HBM-bound"
-            roof = {"bound": "tensor", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TOp/s"}
+            # derived CUDA-core issue ceiling for (add, min): 2 FADD + 1 FMNMX3 per two element-steps
+            # = 1.5 issue slots per step -> 85 steps/clk/SM -> 49.5 TOp/s at 1965 MHz
+            peak = 49.5
+            peak_note = ("derived FP32 add + 3-input min issue ceiling 49.5 TOp/s at 1965 MHz (DESIGN.md 3.3); "
+                         "neither HBM- nor tensor-bound: CUDA-core issue rate")
+            roof = {"bound": "cuda_core_issue", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TOp/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["kernel"] = path
         roof["kernel_ms"] = 1e3 * main_avg_s

@@ -693,7 +693,7 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
     MM_CUDA_TRY(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 8 * cfg.gridDim.x, stream));
   }
   // tuning knobs (diagnostics): ring depth and the TMA loads' L2 eviction priority
-  // Ring depth actually used (<= G::STAGES, the allocation).  Measured (profiles/exp_tile_sync.log,
+  // Ring depth actually used (<= G::STAGES, the allocation).  Measured (profiles/r01_exp_tile_sync.log,
   // float 16384^3 / half 32768^3, CTA pairs, WITH the soft wave barrier): depth 4 leaves the tensor
   // pipe 79-86 % active, depth 5-6 reach 96-98 % at unchanged DRAM traffic (17.7 / 68.8 GB).  Without
   // the barrier depth >= 5 multiplied the DRAM re-reads (27.6 / 31.7 GB at depth 5 / 6, 246 GB for

@@ -1,95 +1,92 @@
-// PrintSpecifications N K M [<SM clock MHz>] — counterpart of the reference's
-// src/PrintSpecifications.cpp:16-80: pure arithmetic on the build configuration, here for the
-// B200 kernels: operation count, the kernel family this configuration dispatches to, its peak
-// model, the ideal runtime and the reference's own communication-volume model
-// Q = N*M*(1 + K/T_N + K/T_M) elements (src/PrintSpecifications.cpp:72-78) with the CTA tile in
-// the role of the FPGA memory tile.
-#include <cstdlib>
-#include <iostream>
+// PrintSpecifications N K M [<SM clock MHz>]
+// Counterpart of the reference's specification printer (src/PrintSpecifications.cpp): pure
+// arithmetic on the build configuration, no device needed.  For the B200 kernels it reports the
+// operation count, the kernel family this configuration dispatches to, that family's pipe-rate
+// model, whole-wave runtime estimates, and the reference's communication-volume model
+//   Q = N*M*(1 + K/T_N + K/T_M) elements            (src/PrintSpecifications.cpp:72-78)
+// evaluated twice: with the CTA tile (bytes through L2) and with the patch of C that the
+// co-running tiles share through L2 (bytes from HBM; profiles/r01_tile_sweep_half32768.csv).
+#include <algorithm>
+#include <iomanip>
 #include <string>
 
-#include "MatrixMultiplication.h"
+#include "HostProblem.h"
 
-static void PrintUsage(char **argv) {
-#ifndef MM_DYNAMIC_SIZES
-  std::cerr << "Usage: " << argv[0] << " [<SM clock MHz>]\n" << std::flush;
-#else
-  std::cerr << "Usage: " << argv[0] << " N K M [<SM clock MHz>]\n" << std::flush;
-#endif
+namespace {
+
+struct KernelModel {
+  std::string family;
+  double ops_per_sm_clock;  // map+reduce operations per SM per clock of the binding pipe
+  unsigned tile_rows, tile_cols, sms_per_tile;
+};
+
+KernelModel ModelFor(std::string const &family) {
+  if (family == "tcgen05_f16") return {family, 2.0 * 4096, 256, 256, 2};   // UMMA 256x256x16 per 128 clk, CTA pair
+  if (family == "tcgen05_tf32") return {family, 2.0 * 2048, 256, 256, 2};  // UMMA 256x256x8  per 128 clk, CTA pair
+  if (family == "dmma_f64") return {family, 2.0 * 64, 128, 128, 1};        // DMMA: 64 FMA / clk / SM
+  return {family, 2.0 * 85, 128, 128, 1};  // CUDA cores: 1.5 issue slots per element-step
 }
 
-int main(int argc, char **argv) {
-#ifdef MM_DYNAMIC_SIZES
-  if (argc > 5 || argc < 4) {
-    PrintUsage(argv);
-    return 1;
-  }
-  const unsigned size_n = std::stoul(argv[1]);
-  const unsigned size_k = std::stoul(argv[2]);
-  const unsigned size_m = std::stoul(argv[3]);
-  int next_arg = 4;
-#else
-  if (argc > 2) {
-    PrintUsage(argv);
-    return 1;
-  }
-  constexpr auto size_n = kSizeN;
-  constexpr auto size_k = kSizeK;
-  constexpr auto size_m = kSizeM;
-  int next_arg = 1;
-#endif
-  float frequency = 1965.0f;  // B200 clocks.max.sm (MHz)
-  if (argc > next_arg) frequency = std::stof(argv[next_arg]);
+template <typename T>
+void Row(const char *label, T const &value, const char *unit = "") {
+  std::cout << std::left << std::setw(28) << label << value << unit << "\n";
+}
 
-  constexpr int kSMs = 148;
-  const std::string path = mm_kernel_path(kDataTypeCode, kMapOpCode, kReduceOpCode, kKernelFlags);
-  // per-SM operations per cycle of the pipe each kernel family is bound by
-  double ops_per_sm_clk;
-  unsigned long tile_n, tile_m;
-  if (path == "tcgen05_f16") {
-    ops_per_sm_clk = 2.0 * 4096;  // 128x256x16 MACs per 128 cycles
-    tile_n = 128; tile_m = 256;
-  } else if (path == "tcgen05_tf32") {
-    ops_per_sm_clk = 2.0 * 2048;  // 128x256x8 MACs per 128 cycles
-    tile_n = 128; tile_m = 256;
-  } else if (path == "dmma_f64") {
-    ops_per_sm_clk = 2.0 * 64;    // FP64 DMMA ~ 64 FMA / clk / SM
-    tile_n = 128; tile_m = 128;
-  } else {
-    ops_per_sm_clk = 2.0 * 64;    // map + reduce: two CUDA-core instructions per element-step, issue bound
-    tile_n = 128; tile_m = 128;
+}  // namespace
+
+int main(int argc, char **argv) {
+  const int required = 1 + mmhost::kShapeArguments;
+  if (argc < required || argc > required + 1) {
+#ifdef MM_DYNAMIC_SIZES
+    std::cerr << "Usage: " << argv[0] << " N K M [<SM clock MHz>]\n" << std::flush;
+#else
+    std::cerr << "Usage: " << argv[0] << " [<SM clock MHz>]\n" << std::flush;
+#endif
+    return 1;
   }
-  const unsigned long long nOps = 2 * static_cast<unsigned long long>(size_n) * size_k * size_m;
-  const double peak = 1e-3 * ops_per_sm_clk * kSMs * frequency;  // GOp/s
-  const unsigned long tiles_n = (size_n + tile_n - 1) / tile_n, tiles_m = (size_m + tile_m - 1) / tile_m;
-  const unsigned long tiles = tiles_n * tiles_m;
-  const unsigned long waves = (tiles + kSMs - 1) / kSMs;
-  const double ideal_runtime = 1e-9 * nOps / peak;
-  // whole waves of full tiles: what the persistent schedule actually executes
-  const double expected_runtime =
-      static_cast<double>(waves) * (2.0 * tile_n * tile_m * size_k) / (ops_per_sm_clk * 1e6 * frequency);
-  std::cout << "Configuration:        " << kDataTypeName << " (" << kMapOpName << ", " << kReduceOpName << ")\n";
-  std::cout << "Kernel family:        " << path << "\n";
-  std::cout << "Frequency:            " << frequency << " MHz\n";
-  std::cout << "Number of operations: " << nOps << " (" << static_cast<float>(nOps) << ")\n";
-  std::cout << "Expected runtime:     " << expected_runtime << " seconds\n";
-  std::cout << "Ideal runtime:        " << ideal_runtime << " seconds\n";
-  std::cout << "Percentage of ideal:  " << 100 * ideal_runtime / expected_runtime << "%\n";
-  std::cout << "Expected performance: " << 1e-9 * nOps / expected_runtime << " GOp/s\n";
-  std::cout << "Ideal performance:    " << peak << " GOp/s\n";
-  std::cout << "Compute tiles: " << tile_n << "x" << tile_m << " per CTA, " << kSMs << " SMs (" << tiles
+  mmhost::Shape s;
+  const int next = mmhost::ReadShape(argv, 1, &s);
+  const double mhz = next < argc ? std::stod(argv[next]) : 1965.0;  // B200 clocks.max.sm
+  constexpr unsigned kSMs = 148;
+
+  const KernelModel model = ModelFor(mm_kernel_path(kDataTypeCode, kMapOpCode, kReduceOpCode, kKernelFlags));
+  const double ops = 2.0 * s.n * static_cast<double>(s.k) * s.m;
+  const double peak_gops = 1e-3 * model.ops_per_sm_clock * kSMs * mhz;
+  const unsigned long tiles_n = (s.n + model.tile_rows - 1) / model.tile_rows;
+  const unsigned long tiles_m = (s.m + model.tile_cols - 1) / model.tile_cols;
+  const unsigned long slots = kSMs / model.sms_per_tile;
+  const unsigned long waves = (tiles_n * tiles_m + slots - 1) / slots;
+  const double tile_seconds =
+      2.0 * model.tile_rows * model.tile_cols * s.k / (model.ops_per_sm_clock * model.sms_per_tile * 1e6 * mhz);
+  const double ideal = 1e-9 * ops / peak_gops, expected = waves * tile_seconds;
+
+  Row("Configuration:", std::string(kDataTypeName) + " (" + kMapOpName + ", " + kReduceOpName + ")");
+  Row("Kernel family:", model.family);
+  Row("Frequency:", mhz, " MHz");
+  Row("Number of operations:", ops);
+  Row("Ideal performance:", peak_gops, " GOp/s");
+  Row("Ideal runtime:", ideal, " seconds");
+  Row("Expected runtime:", expected, " seconds (whole waves of full tiles)");
+  Row("Percentage of ideal:", 100.0 * ideal / expected, "%");
+  Row("Expected performance:", 1e-9 * ops / expected, " GOp/s");
+  std::cout << "Compute tiles: " << model.tile_rows << "x" << model.tile_cols << " per "
+            << (model.sms_per_tile == 2 ? "CTA pair" : "CTA") << ", " << kSMs << " SMs (" << tiles_n * tiles_m
             << " tiles, " << waves << " waves)\n";
-  std::cout << "Tiles in N: " << tiles_n << "\n";
-  std::cout << "Tiles in M: " << tiles_m << "\n";
-  const unsigned long long communicationVolume =
-      static_cast<unsigned long long>(size_n) * size_m * (1 + size_k / tile_n + size_k / tile_m);
-  std::cout << "Communication volume: " << communicationVolume << " elements ("
-            << 1e-9 * communicationVolume * sizeof(Data_t) << " GB through L2 at this tile size)\n";
-  const double ioAccesses = communicationVolume / (3 * static_cast<double>(size_n) * size_m * size_k);
-  std::cout << "I/O access fraction: " << ioAccesses << "\n";
-  const unsigned long long algorithmic =
-      (static_cast<unsigned long long>(size_n) * size_k + static_cast<unsigned long long>(size_k) * size_m +
-       static_cast<unsigned long long>(size_n) * size_m) * sizeof(Data_t);
-  std::cout << "Algorithmic bytes:    " << algorithmic << "\n";
+  Row("Tiles in N:", tiles_n);
+  Row("Tiles in M:", tiles_m);
+
+  auto volume = [&](double t_n, double t_m) { return static_cast<double>(s.n) * s.m * (1 + s.k / t_n + s.k / t_m); };
+  const double through_l2 = volume(model.tile_rows, model.tile_cols);
+  // patch shared through L2: 2048 rows (rasterisation group) x the columns the other tiles cover
+  const double patch_rows = std::min<double>(2048, s.n);
+  const double patch_cols = std::min<double>(s.m, std::max<double>(model.tile_cols, slots * model.tile_rows / patch_rows * model.tile_cols));
+  const double from_hbm = volume(patch_rows, patch_cols);
+  Row("Communication volume:", through_l2, " elements through L2 (CTA tile)");
+  Row("", 1e-9 * through_l2 * sizeof(Data_t), " GB");
+  Row("HBM volume model:", from_hbm, " elements (L2 patch as memory tile)");
+  Row("", 1e-9 * from_hbm * sizeof(Data_t), " GB");
+  Row("I/O access fraction:", through_l2 / (3.0 * s.n * s.m * s.k));
+  Row("Algorithmic bytes:", (static_cast<double>(s.n) * s.k + static_cast<double>(s.k) * s.m +
+                             static_cast<double>(s.n) * s.m) * sizeof(Data_t));
   return 0;
 }

@@ -103,10 +103,16 @@ def main():
         open(os.path.join(dst, "%s_%s.txt" % (tag, base)), "w").write("\n".join(lines) + "\n")
     json.dump(traffic, open(tpath, "w"), indent=1, sort_keys=True)
 
-    for extra in ("pytest_gpu.log", "host_executables.log", "gpu.txt"):
+    extras = ["pytest_gpu.log", "host_executables.log", "gpu.txt", "cpu_baseline.json"]
+    for pat in ("scale_*.json", "multi_runhardware_*.log", "tile_sweep_*.csv"):
+        extras += [os.path.basename(x) for x in glob.glob(os.path.join(src, pat))]
+    for extra in extras:
         p = os.path.join(src, extra)
         if os.path.exists(p):
             open(os.path.join(dst, "%s_%s" % (tag, extra)), "w").write(open(p).read())
+    # diagnostics written by the scripts/exp_*.sh experiments
+    for p in glob.glob(os.path.join(ROOT, "gpurun_out", "exp_*")):
+        open(os.path.join(dst, "%s_%s" % (tag, os.path.basename(p))), "w").write(open(p).read())
     print("profiles/ updated from", src)
 
 
