@@ -1,0 +1,11 @@
+#!/bin/bash
+# compute-sanitizer passes over small ragged invocations of every kernel family + the new tests
+set +e
+mkdir -p gpurun_out/r01
+O=gpurun_out/r01
+echo "== new tests"; timeout 600 python -m pytest tests/test_parity_gpu.py -q -m gpu -k "graph or two_contexts" 2>&1 | tail -5
+for tool in memcheck racecheck synccheck; do
+  echo "== compute-sanitizer $tool"
+  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python scripts/sanitize_small.py > $O/sanitizer_$tool.log 2>&1
+  echo "rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|ok$|MISMATCH|Error|hazard" $O/sanitizer_$tool.log | sort | uniq -c | head -20
+done

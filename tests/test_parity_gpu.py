@@ -255,3 +255,58 @@ def test_row_block_split_equals_single_launch(mm, oracle):
     top = mm.matrix_multiplication_kernel(a2[:256], b, 256, k, m)
     bot = mm.matrix_multiplication_kernel(a2[256:], b, 256, k, m)
     assert np.concatenate([top, bot]).tobytes() == whole.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------
+# 5. streams and graphs: the asynchronous entry on a caller-owned stream, CUDA-graph capture
+# ---------------------------------------------------------------------------------------------
+def test_enqueue_on_caller_stream_and_graph_replay(mm, oracle):
+    """mm_kernel_enqueue on a caller-owned stream is capturable into a CUDA graph once the context's
+    scratch exists (first call outside capture); replaying the graph recomputes C from new A."""
+    torch = pytest.importorskip("torch")
+    n, k, m = 384, 512, 640
+    a, b = oracle.fill(oracle.FLOAT, n, k, m)
+    ref = oracle.naive(oracle.FLOAT, oracle.MULTIPLY, oracle.ADD, a, b, n, k, m, threads=8)
+    dev = torch.device("cuda", 0)
+    ta = torch.from_numpy(a.reshape(n, k)).to(dev)
+    tb = torch.from_numpy(b.reshape(k, m)).to(dev)
+    tc = torch.zeros((n, m), device=dev, dtype=torch.float32)
+    with mm.Context(0) as ctx:
+        s = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(s):
+            ctx.enqueue(mm.FLOAT, mm.MULTIPLY, mm.ADD, ta.data_ptr(), tb.data_ptr(), tc.data_ptr(), n, k, m,
+                        stream=s.cuda_stream)          # warm-up: allocates the scratch, loads the kernels
+        s.synchronize()
+        assert oracle.verify(oracle.FLOAT, tc.cpu().numpy(), ref) == -1
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            ctx.enqueue(mm.FLOAT, mm.MULTIPLY, mm.ADD, ta.data_ptr(), tb.data_ptr(), tc.data_ptr(), n, k, m,
+                        stream=torch.cuda.current_stream().cuda_stream)
+        ta.mul_(2.0)                                    # new input, same buffers
+        tc.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        got = tc.cpu().numpy()
+    assert oracle.verify(oracle.FLOAT, got, (2.0 * ref).astype(np.float32)) == -1
+
+
+def test_two_contexts_on_two_streams_do_not_interfere(mm, oracle):
+    """Contexts own their scratch: two contexts running different problems back to back on their
+    own streams give the same bits as running alone."""
+    shapes = [(256, 512, 384, mm.FLOAT, mm.MULTIPLY, mm.ADD), (200, 256, 512, mm.FLOAT, mm.ADD, mm.MIN)]
+    alone, data = [], []
+    for n, k, m, dt, mp, rd in shapes:
+        a, b = oracle.fill(dt, n, k, m, 21)
+        data.append((a, b))
+        alone.append(mm.matrix_multiplication_kernel(a, b, n, k, m, dtype=dt, map_op=mp, reduce_op=rd))
+    ctxs = [mm.Context(0), mm.Context(0)]
+    try:
+        outs = []
+        for rep in range(3):
+            outs = [ctxs[i].gemm_host(dt, mp, rd, data[i][0], data[i][1], n, k, m)[0]
+                    for i, (n, k, m, dt, mp, rd) in enumerate(shapes)]
+        for o, ref in zip(outs, alone):
+            assert o.tobytes() == ref.tobytes()
+    finally:
+        for c in ctxs:
+            c.close()
