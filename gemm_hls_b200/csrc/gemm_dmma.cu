@@ -10,6 +10,7 @@
 // reads of each half-warp hit 16 distinct 8-byte banks.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -44,18 +45,24 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                : "d"(a), "d"(b));
 }
 
-template <bool TRANSPOSED_A>
-__global__ void __launch_bounds__(256, 1)
+// WM x WN warps; each warp owns a (BM / WM) x (BN / WN) block of C as MI x NJ m8n8 accumulator tiles.
+// 2 x 4 warps (64 x 32 per warp, 64 accumulators per thread) minimises fragment loads per DMMA;
+// 4 x 4 warps (32 x 32 per warp, 32 accumulators) doubles the warps per scheduler.
+template <bool TRANSPOSED_A, int WM, int WN>
+__global__ void __launch_bounds__(WM * WN * 32, 1)
 gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C,
                  unsigned size_n, unsigned size_k, unsigned size_m) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *As = reinterpret_cast<double *>(smem_raw);
   double *Bs = As + STAGES * A_TILE;
 
+  constexpr int THREADS = WM * WN * 32;
+  constexpr int MI = BM / (WM * 8);  // m8n8 tiles per warp along M
+  constexpr int NJ = BN / (WN * 8);  // ... along N
   const int tid = threadIdx.x;
   const int warp = tid / 32, lane = tid % 32;
-  const int wr = warp / 4;  // 0..1  -> rows [64*wr, +64)
-  const int wc = warp % 4;  // 0..3  -> cols [32*wc, +32)
+  const int wr = warp / WN;  // warp row    -> rows [wr * MI * 8, +MI * 8)
+  const int wc = warp % WN;  // warp column -> cols [wc * NJ * 8, +NJ * 8)
   const int g = lane / 4;   // fragment row / col within an 8-wide tile
   const int q = lane % 4;   // fragment k index
   const size_t row0 = size_t(blockIdx.y) * BM;
@@ -67,8 +74,8 @@ gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, dou
     if (!TRANSPOSED_A) {
       // 128 rows x BK doubles as 16-byte chunks; BK / 2 chunks per row
 #pragma unroll
-      for (int i = 0; i < BM * BK / 2 / 256; ++i) {
-        const int c = tid + i * 256;
+      for (int i = 0; i < BM * BK / 2 / THREADS; ++i) {
+        const int c = tid + i * THREADS;
         const int r = c / (BK / 2), part = c % (BK / 2);
         size_t row = row0 + r;
         if (row >= size_n) row = size_n - 1;
@@ -79,8 +86,8 @@ gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, dou
     } else {
       // BK k-rows x 128 n-cols; 64 chunks per row
 #pragma unroll
-      for (int i = 0; i < BK * BM / 2 / 256; ++i) {
-        const int c = tid + i * 256;
+      for (int i = 0; i < BK * BM / 2 / THREADS; ++i) {
+        const int c = tid + i * THREADS;
         const int kk = c / 64, part = c % 64;
         size_t n = row0 + part * 2;
         if (n + 2 > size_n) n = size_n - 2;  // N % 2 == 0 checked by the launcher
@@ -89,8 +96,8 @@ gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, dou
       }
     }
 #pragma unroll
-    for (int i = 0; i < BK * BN / 2 / 256; ++i) {
-      const int c = tid + i * 256;
+    for (int i = 0; i < BK * BN / 2 / THREADS; ++i) {
+      const int c = tid + i * THREADS;
       const int kk = c / 64, part = c % 64;
       size_t col = col0 + part * 2;
       if (col + 2 > size_m) col = size_m - 2;
@@ -99,11 +106,11 @@ gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, dou
     }
   };
 
-  double acc[8][4][2];
+  double acc[MI][NJ][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const unsigned k_tiles = (size_k + BK - 1) / BK;
 #pragma unroll
@@ -124,30 +131,30 @@ gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, dou
     const double *bs = Bs + (kt % STAGES) * B_TILE;
 #pragma unroll
     for (int k4 = 0; k4 < BK; k4 += 4) {
-      double af[8], bf[4];
+      double af[MI], bf[NJ];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = wr * 64 + i * 8 + g;
+      for (int i = 0; i < MI; ++i) {
+        const int r = wr * MI * 8 + i * 8 + g;
         af[i] = TRANSPOSED_A ? as[(k4 + q) * LDAT_S + r] : as[r * LDA_S + k4 + q];
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = bs[(k4 + q) * LDB_S + wc * 32 + j * 8 + g];
+      for (int j = 0; j < NJ; ++j) bf[j] = bs[(k4 + q) * LDB_S + wc * NJ * 8 + j * 8 + g];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
 
   // C fragment of m8n8: thread holds (row g, cols 2q, 2q+1)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const size_t row = row0 + wr * 64 + i * 8 + g;
+  for (int i = 0; i < MI; ++i) {
+    const size_t row = row0 + wr * MI * 8 + i * 8 + g;
     if (row >= size_n) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const size_t col = col0 + wc * 32 + j * 8 + q * 2;
+    for (int j = 0; j < NJ; ++j) {
+      const size_t col = col0 + wc * NJ * 8 + j * 8 + q * 2;
       if (col + 2 <= size_m) {
         *reinterpret_cast<double2 *>(C + row * size_m + col) = make_double2(acc[i][j][0], acc[i][j][1]);
       }
@@ -155,25 +162,36 @@ gemm_dmma_kernel(const double *__restrict__ A, const double *__restrict__ B, dou
   }
 }
 
-}  // namespace
-
-int launch_dmma(const GemmArgs &g) {
+template <int WM, int WN>
+static int launch_dmma_variant(const GemmArgs &g) {
   const bool ta = (g.flags & MM_FLAG_TRANSPOSED_A) != 0;
-  if (ta && (g.n % 2 != 0)) return fail(MM_ERR_UNSUPPORTED, "dmma path with transposed A needs even N");
-  MM_CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-  MM_CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+  MM_CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<false, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+  MM_CUDA_TRY(cudaFuncSetAttribute(gemm_dmma_kernel<true, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
   if (g.dry_run) return MM_OK;
   dim3 grid(ceil_div(g.m, BN), ceil_div(g.n, BM));
   const double *a = static_cast<const double *>(g.a);
   const double *b = static_cast<const double *>(g.b);
   double *c = static_cast<double *>(g.c);
   if (ta) {
-    gemm_dmma_kernel<true><<<grid, 256, SMEM_BYTES, g.stream>>>(a, b, c, g.n, g.k, g.m);
+    gemm_dmma_kernel<true, WM, WN><<<grid, WM * WN * 32, SMEM_BYTES, g.stream>>>(a, b, c, g.n, g.k, g.m);
   } else {
-    gemm_dmma_kernel<false><<<grid, 256, SMEM_BYTES, g.stream>>>(a, b, c, g.n, g.k, g.m);
+    gemm_dmma_kernel<false, WM, WN><<<grid, WM * WN * 32, SMEM_BYTES, g.stream>>>(a, b, c, g.n, g.k, g.m);
   }
   MM_CUDA_TRY(cudaGetLastError());
   return MM_OK;
+}
+
+}  // namespace
+
+int launch_dmma(const GemmArgs &g) {
+  const bool ta = (g.flags & MM_FLAG_TRANSPOSED_A) != 0;
+  if (ta && (g.n % 2 != 0)) return fail(MM_ERR_UNSUPPORTED, "dmma path with transposed A needs even N");
+  // MM_DMMA_WARPS=8 selects the 2 x 4 warp layout for A/B measurements (default 16 = 4 x 4)
+  static const int warps = [] {
+    const char *e = std::getenv("MM_DMMA_WARPS");
+    return (e && std::atoi(e) == 8) ? 8 : 16;
+  }();
+  return warps == 8 ? launch_dmma_variant<2, 4>(g) : launch_dmma_variant<4, 4>(g);
 }
 
 }  // namespace mm

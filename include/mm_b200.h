@@ -125,7 +125,10 @@ MM_API int mm_kernel_execute(mm_context *ctx, int dtype, int map_op, int reduce_
 
 /* Same launch, asynchronous on a caller-supplied CUDA stream (cudaStream_t passed as void*; NULL =
  * the context's own stream), no timing, no synchronisation: for callers that own the stream
- * (benchmark loops, CUDA-graph capture, multi-GPU row-block drivers). */
+ * (benchmark loops, CUDA-graph capture, multi-GPU row-block drivers).  The context's scratch is
+ * shared by everything enqueued through it: keep the work of ONE context stream-ordered (one stream
+ * at a time) and use one context per concurrently running stream.  Capturable into a CUDA graph
+ * once a first call outside capture has sized the scratch. */
 MM_API int mm_kernel_enqueue(mm_context *ctx, int dtype, int map_op, int reduce_op, int flags,
                       const void *a_device, const void *b_device, void *c_device, unsigned size_n,
                       unsigned size_k, unsigned size_m, void *cuda_stream);
