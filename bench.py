@@ -97,9 +97,11 @@ class ClockSampler:
                     reasons.add(name)
         # keep the samples taken under load (power above the idle floor) when there are any
         loaded = [s for s, p in zip(sm, power) if p > 300.0] or sm
+        loaded_power = [p for p in power if p > 300.0]
         return {"sm_mhz": statistics.median(loaded) if loaded else None,
                 "sm_max_mhz": max(smmax) if smmax else None,
                 "power_w_max": max(power) if power else None,
+                "power_w_avg_under_load": (sum(loaded_power) / len(loaded_power)) if loaded_power else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -316,6 +318,11 @@ def main():
                                               "half": "f16 multiply, f32 accumulate", "double": "f64"}[dtype_name]
                if (mp_name, rd_name) == ("Multiply", "Add") else "f32",
                "data": "synthetic", "config": config, "clocks": clocks, "roofline": roof,
+               # NVML board power during the timed region (the reference's PSU power meter);
+               # meaningful for runs of a second or more (nvidia-smi refreshes every ~100 ms)
+               "energy": ({"avg_power_w": clocks["power_w_avg_under_load"],
+                           "gop_per_joule": value / clocks["power_w_avg_under_load"]}
+                          if clocks and clocks.get("power_w_avg_under_load") else None),
                "gpu_launches": args.steps * G.launch_count(dtype, mp, rd, flags)}
 
     # ------------------------------------------------------------------ e2e: host buffers through the C-ABI

@@ -5,12 +5,15 @@
 //   hw      the B200 selected by $MM_DEVICE (default 0)
 //   hw_emu  accepted for compatibility; there is no emulation target, it runs on the B200 as well
 //   MM_NUM_GPUS=G (> 1, build with NCCL)  row-block split over G GPUs, B broadcast once (MultiGpu.h)
+//   MM_POWER_METER=1  NVML power sampling every 10 ms while the kernel is repeated for >= 2 s, then
+//                     the reference's "Measured an average power of ... W" line (host/RunHardware.cpp:182-185)
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
 
 #include "Device.h"
 #include "HostProblem.h"
+#include "PowerMeter.h"
 #ifdef MM_HAS_NCCL
 #include "MultiGpu.h"
 #endif
@@ -81,7 +84,24 @@ void RunSingle(mmhost::Problem &problem, bool verify) {
   auto kernel = context.MakeKernel(kDataTypeCode, kMapOpCode, kReduceOpCode, kKernelFlags, a_device, b_device,
                                    c_device, shape.n, shape.k, shape.m);
   std::cout << "Executing kernel...\n" << std::flush;
-  ReportPerformance(shape, kernel.ExecuteTask().first);
+  if (EnvironmentInt("MM_POWER_METER", 0) != 0) {
+    // A B200 kernel lasts milliseconds and NVML refreshes its reading every ~100 ms: repeat the
+    // launch for at least two seconds under the meter and report the last run's time.
+    mm::PowerMeter meter(10, static_cast<unsigned>(EnvironmentInt("MM_DEVICE", 0)));  // 10 ms, as the reference
+    double device_seconds = 0, total = 0;
+    meter.Start();
+    do {
+      device_seconds = kernel.ExecuteTask().first;
+      total += device_seconds;
+    } while (total < 2.0);
+    meter.Stop();
+    ReportPerformance(shape, device_seconds);
+    const double watts = meter.AveragePower();
+    std::cout << "Measured an average power of " << watts << " W for the GPU ("
+              << 1e-9 * shape.Operations() / device_seconds / watts << " GOp/J).\n";
+  } else {
+    ReportPerformance(shape, kernel.ExecuteTask().first);
+  }
   if (verify) {
     std::cout << "Copying back result...\n" << std::flush;
     c_device.CopyToHost(problem.Result());

@@ -35,7 +35,7 @@ PY
 R=${GRAFT_REPO_ROOT:-/root/repo}
 for exe in TestSimulation RunHardware PrintSpecifications; do
   src=$R/gemm_hls_b200/host/$exe.cpp; extra=""; [ $exe = TestSimulation ] && extra=$R/gemm_hls_b200/host/KernelEntry.cpp
-  g++ -std=c++17 -O2 -DMM_DYNAMIC_SIZES -I. -I$R/include -I$R/gemm_hls_b200/host $src $extra -L$R/gemm_hls_b200 -lmm_b200 -Wl,-rpath,$R/gemm_hls_b200 -o $exe || echo "build of $exe failed"
+  g++ -std=c++17 -O2 -DMM_DYNAMIC_SIZES -I. -I$R/include -I$R/gemm_hls_b200/host $src $extra -L$R/gemm_hls_b200 -lmm_b200 -Wl,-rpath,$R/gemm_hls_b200 -ldl -lpthread -o $exe || echo "build of $exe failed"
 done
 cd $R
 ( /tmp/hostbuild/TestSimulation 513 528 528; echo "TestSimulation rc=$?"; /tmp/hostbuild/RunHardware 2048 2048 2048 hw on; echo "RunHardware rc=$?"; /tmp/hostbuild/RunHardware 16384 16384 16384 hw off; echo "RunHardware rc=$?"; /tmp/hostbuild/PrintSpecifications 16384 16384 16384 ) > $O/host_executables.log 2>&1; tail -22 $O/host_executables.log
