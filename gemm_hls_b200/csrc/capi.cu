@@ -316,7 +316,7 @@ int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags) {
     case kPathTcgen05:
       // [B^T prep unless B is read directly] + [A prep for float or transposed A] + GEMM
       return 1 + (mm::tcgen05_b_direct(dtype) ? 0 : 1) +
-             ((dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) ? 1 : 0);
+             (((dtype == MM_DTYPE_FLOAT && !mm::tcgen05_fuse_a(dtype, flags)) || (flags & MM_FLAG_TRANSPOSED_A)) ? 1 : 0);
     case kPathDmma: return 1;
     case kPathSemiring: return 1;
   }
@@ -418,14 +418,16 @@ int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flag
     const void *a_chunk = da + (ta ? 0 : r0 * k * es);
     void *c_chunk = dc + r0 * m * es;
     if (path == kPathTcgen05) {
-      const void *a_op = nullptr;
+      const void *a_op = nullptr, *a_raw = nullptr;
       const size_t a_scale = (dtype == MM_DTYPE_FLOAT && (flags & MM_FLAG_TF32X3)) ? 3 : 1;
       rc = mm::tcgen05_prepare_a(dtype, a_chunk, aprep + (ta ? 0 : r0 * k * es * a_scale), unsigned(rows), k, flags,
-                                 &a_op, ctx->stream);
+                                 &a_op, &a_raw, ctx->stream);
       if (rc != MM_OK) return rc;
-      unsigned int *tile_sync = reinterpret_cast<unsigned int *>(
-          static_cast<unsigned char *>(ctx->scratch.ptr) + ctx->scratch.bytes - 256);
-      rc = mm::tcgen05_gemm(dtype, a_op, b_op, c_chunk, unsigned(rows), k, m, flags, tile_sync, ctx->stream);
+      unsigned char *tail = static_cast<unsigned char *>(ctx->scratch.ptr) + ctx->scratch.bytes;
+      unsigned int *tile_sync = reinterpret_cast<unsigned int *>(tail - 256);
+      unsigned int *a_done = reinterpret_cast<unsigned int *>(tail - mm::kTcgen05TailBytes);
+      rc = mm::tcgen05_gemm(dtype, a_op, b_op, c_chunk, unsigned(rows), k, m, flags, tile_sync, a_raw, a_done,
+                            ctx->stream);
     } else {
       mm::GemmArgs g{a_chunk, db, c_chunk, unsigned(rows), k, m, flags, ctx->stream};
       rc = (path == kPathDmma) ? mm::launch_dmma(g) : mm::launch_semiring(dtype, map_op, reduce_op, g);

@@ -64,11 +64,15 @@ int launch_tcgen05(int dtype, const GemmArgs &args, void *scratch, size_t scratc
 int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m, int flags,
                       const void **b_op, cudaStream_t stream);
 bool tcgen05_b_direct(int dtype);
+bool tcgen05_fuse_a(int dtype, int flags);
+// *a_raw != nullptr on return: nothing was launched, the GEMM kernel itself rounds *a_raw into *a_op.
 int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, int flags,
-                      const void **a_op, cudaStream_t stream);
+                      const void **a_op, const void **a_raw, cudaStream_t stream);
 // `tile_sync`: device counter (zeroed by the launcher) for the kernel's soft wave barrier, or null.
 int tcgen05_gemm(int dtype, const void *a_op, const void *b_op, void *c, unsigned rows, unsigned k,
-                 unsigned m, int flags, unsigned int *tile_sync, cudaStream_t stream);
+                 unsigned m, int flags, unsigned int *tile_sync, const void *a_raw, unsigned int *counters,
+                 cudaStream_t stream);
+constexpr size_t kTcgen05TailBytes = 256 + 64 * 1024;  // [granule counters][wave-barrier counter] at the scratch tail
 
 // DMMA (mma.sync m8n8k4 f64) GEMM for (Multiply, Add) double.  gemm_dmma.cu
 int launch_dmma(const GemmArgs &args);

@@ -111,6 +111,12 @@ __device__ __forceinline__ void store_chunk<__half>(__half *crow, const uint32_t
   }
 }
 
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -125,12 +131,27 @@ __device__ __forceinline__ void cluster_sync_all() {
 // BMN: the B operand is read MN-major straight from the reference's row-major B (K x M) — no
 // transposed copy.  Implemented for kind::f16 (64-element atoms); kind::tf32 needs B rounded to
 // TF32 anyway, so its prepared copy is written K-major.
-template <int KIND, typename TOut, int CG, bool BMN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// FUSE_A (float only): the TF32 rounding of A runs INSIDE this kernel on four extra warps of every
+// CTA.  They sweep A in row order in granules of PREP_ROWS rows (all CTAs share each granule), write
+// the rounded copy that tmap_a describes, and count finished granules in `fuse.a_done`; the TMA
+// producer starts a tile only when its granule is complete.  Only the first granules are exposed
+// (the GEMM consumes 2048 rows per ~1.2 ms, the sweep rounds the whole of A in ~0.5 ms).
+struct FuseA {
+  const float4 *a_raw;    // caller's A (row-major rows x k)
+  float4 *a_prep;         // rounded copy (what tmap_a points at)
+  unsigned int *a_done;   // one counter per granule, zeroed by the launcher; complete == gridDim.x
+  uint32_t k_elems;
+  uint32_t late_warps;    // rounding warps per CTA that keep working after the first raster group (1..4)
+};
+constexpr int PREP_WARPS = 4;
+constexpr int PREP_ROWS = 256;   // granule height = pair-tile height, so a CTA's 128 rows lie in one granule
+
+template <int KIND, typename TOut, int CG, bool BMN, bool FUSE_A>
+__global__ void __launch_bounds__(NUM_THREADS + (FUSE_A ? PREP_WARPS * 32 : 0), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, TOut *__restrict__ C, uint32_t rows,
                     uint32_t cols, uint32_t k_bytes, uint32_t num_stages, uint32_t raster_group,
-                    uint64_t l2_policy, unsigned int *tile_sync, unsigned long long *dbg) {
+                    uint64_t l2_policy, unsigned int *tile_sync, FuseA fuse, unsigned long long *dbg) {
   using G = Geo<CG>;
   const int STAGES = int(num_stages);  // <= G::STAGES (what the shared-memory allocation holds)
   extern __shared__ unsigned char smem_raw[];
@@ -193,6 +214,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t stage = 0, phase = 0;
       long long wait_empty = 0, t_begin = clock64();
       uint32_t tile_iter = 0;
+      int32_t a_ready = -1;
       for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++tile_iter) {
         // Soft wave barrier: do not start fetching tile #j before every CTA group has finished
         // fetching its tile #(j-1).  A ring deep enough to hide DRAM latency removes the L2-miss
@@ -209,6 +231,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const TileCoord tc = tile_coord(t, tiles_r, tiles_c, raster_group);
         const int32_t a_row = tc.r * G::TILE_ROWS + cta_rank * BLOCK_M;
         const int32_t b_row = tc.c * BLOCK_N + cta_rank * G::LOAD_N;
+        if (FUSE_A) {
+          // rows [a_row, a_row + 128) lie in granule a_row / PREP_ROWS; granules complete in order
+          const int32_t granule = a_row / PREP_ROWS;
+          if (granule > a_ready) {
+            // All CTAs of this persistent grid are resident (grid <= SMs, 1 CTA per SM), so the
+            // rounding warps of every CTA make progress while this thread spins.  The bound only
+            // turns an impossible-to-satisfy wait (e.g. a tool that serialises CTAs) into a trap.
+            const volatile unsigned int *flag = fuse.a_done + granule;
+            const long long t0 = clock64();
+            while (*flag < gridDim.x) {
+              if (clock64() - t0 > (1ll << 33)) __trap();
+            }
+            __threadfence();
+            asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes -> TMA reads
+            a_ready = granule;
+          }
+        }
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
           if (dbg) {
             const long long t0 = clock64();
@@ -313,6 +352,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
       }
     }
+  } else if (FUSE_A && warp >= NUM_THREADS / 32) {
+    // ================= A rounding (warps 6..9 of every CTA) =================
+    const uint32_t pt = threadIdx.x - NUM_THREADS;             // 0..127 within the CTA's prep group
+    const uint32_t k4 = fuse.k_elems / 4;
+    const uint32_t granules = (rows + PREP_ROWS - 1) / PREP_ROWS;
+    // The first raster group (what the first wave of tiles needs) is rounded at full speed by all
+    // four warps; after that the GEMM consumes 2048 rows per ~1.2 ms, so only `late_warps` warps
+    // keep sweeping: less HBM / L2 pressure on the GEMM's own loads.  Streaming (evict-first)
+    // accesses keep the sweep from displacing the A / B^T panels the co-running tiles share in L2.
+    const uint32_t first_granules = RASTER_GROUP_ROWS / PREP_ROWS;
+    for (uint32_t gr = 0; gr < granules; ++gr) {
+      const uint32_t active = (gr < first_granules) ? uint32_t(PREP_WARPS) : fuse.late_warps;
+      const size_t begin = size_t(gr) * PREP_ROWS * k4;
+      const size_t end = size_t(min(rows, (gr + 1) * PREP_ROWS)) * k4;
+      if (pt < active * 32) {
+        const size_t stride = size_t(gridDim.x) * (active * 32);
+        size_t i = begin + size_t(blockIdx.x) * (active * 32) + pt;
+        for (; i + 7 * stride < end; i += 8 * stride) {  // 8 independent 16-byte loads in flight per thread
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldcs(fuse.a_raw + i + u * stride);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            v[u].x = round_tf32(v[u].x); v[u].y = round_tf32(v[u].y);
+            v[u].z = round_tf32(v[u].z); v[u].w = round_tf32(v[u].w);
+            __stcs(fuse.a_prep + i + u * stride, v[u]);
+          }
+        }
+        for (; i < end; i += stride) {
+          float4 v = __ldcs(fuse.a_raw + i);
+          v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+          __stcs(fuse.a_prep + i, v);
+        }
+        __threadfence();                                        // this thread's stores visible GPU-wide
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(PREP_WARPS * 32) : "memory");  // the CTA's prep warps only
+      if (pt == 0) atomicAdd(fuse.a_done + gr, 1u);
+    }
   } else {
     // ================= epilogue (warps 2..5 of every CTA) =================
     const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, +32) are this warp's
@@ -351,11 +428,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 // ---- operand preparation ------------------------------------------------------------------------
-__device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 // dst[i] = rna_tf32(src[i]); count is a multiple of 4 (K % 16 == 0).
 __global__ void __launch_bounds__(256)
@@ -553,7 +625,10 @@ void launch_transpose(const void *src, void *dst, uint32_t src_rows, uint32_t sr
 
 }  // namespace
 
-constexpr size_t TILE_SYNC_BYTES = 256;  // the soft wave-barrier counter lives in the LAST 256 bytes of the scratch
+// Tail of the scratch: [granule counters of the fused A rounding, 64 KiB][soft wave-barrier counter, 256 B]
+constexpr size_t TILE_SYNC_BYTES = 256;
+constexpr size_t A_DONE_BYTES = 64 * 1024;  // 16384 granules of 256 rows = 4 Mi rows
+constexpr size_t TAIL_BYTES = TILE_SYNC_BYTES + A_DONE_BYTES;
 
 static bool split3(int dtype, int flags) { return dtype == MM_DTYPE_FLOAT && (flags & MM_FLAG_TF32X3); }
 
@@ -575,7 +650,7 @@ size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m, int flags) {
 
 size_t tcgen05_scratch_bytes(int dtype, unsigned n, unsigned k, unsigned m, int flags) {
   const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
-  size_t bytes = TILE_SYNC_BYTES + tcgen05_bt_bytes(dtype, k, m, flags);  // wave-barrier counter (tail) + B^T
+  size_t bytes = TAIL_BYTES + tcgen05_bt_bytes(dtype, k, m, flags);  // counters (tail) + B^T
   if (dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) {
     bytes += align_up(size_t(n) * k * eb * (split3(dtype, flags) ? 3 : 1), 1024);
   }
@@ -618,9 +693,16 @@ int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m
 // half A is used in place; A stored K x N (`transposed`, leading dimension n_total, only whole
 // matrices) is transposed into `aprep`.  *a_op receives the operand pointer.
 int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, int flags,
-                      const void **a_op, cudaStream_t stream) {
+                      const void **a_op, const void **a_raw, cudaStream_t stream) {
   const bool transposed = (flags & MM_FLAG_TRANSPOSED_A) != 0;
   *a_op = a;
+  *a_raw = nullptr;
+  if (tcgen05_fuse_a(dtype, flags) && size_t(rows) / PREP_ROWS < A_DONE_BYTES / sizeof(unsigned int)) {
+    // the GEMM kernel rounds A into `aprep` itself
+    *a_op = aprep;
+    *a_raw = a;
+    return MM_OK;
+  }
   if (split3(dtype, flags)) {
     if (transposed) {
       dim3 grid((rows + 63) / 64, (k + 63) / 64);
@@ -665,17 +747,18 @@ static int cta_group_choice() {
   return v;
 }
 
-template <int KIND, typename TOut, int CG, bool BMN>
+template <int KIND, typename TOut, int CG, bool BMN, bool FUSE_A>
 static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_b, void *c, unsigned rows,
-                               unsigned m, uint32_t k_bytes, unsigned int *tile_sync, cudaStream_t stream) {
+                               unsigned m, uint32_t k_bytes, unsigned int *tile_sync, FuseA fuse,
+                               cudaStream_t stream) {
   using G = Geo<CG>;
-  auto kern = gemm_tcgen05_kernel<KIND, TOut, CG, BMN>;
+  auto kern = gemm_tcgen05_kernel<KIND, TOut, CG, BMN, FUSE_A>;
   MM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G::SMEM_BYTES)));
   const uint32_t tiles = ceil_div(rows, G::TILE_ROWS) * ceil_div(m, BLOCK_N);
   const uint32_t groups = std::min<uint32_t>(tiles, uint32_t(num_sms()) / CG);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * CG);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(NUM_THREADS + (FUSE_A ? PREP_WARPS * 32 : 0));
   cfg.dynamicSmemBytes = G::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -724,8 +807,12 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
   }();
   if (!use_tile_sync) tile_sync = nullptr;
   if (tile_sync) MM_CUDA_TRY(cudaMemsetAsync(tile_sync, 0, sizeof(unsigned int), stream));
+  if (FUSE_A) {
+    const size_t granules = (size_t(rows) + PREP_ROWS - 1) / PREP_ROWS;
+    MM_CUDA_TRY(cudaMemsetAsync(fuse.a_done, 0, granules * sizeof(unsigned int), stream));
+  }
   MM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, static_cast<TOut *>(c), uint32_t(rows), uint32_t(m),
-                                 k_bytes, stages, raster_group, l2_policy, tile_sync, dbg));
+                                 k_bytes, stages, raster_group, l2_policy, tile_sync, fuse, dbg));
   if (debug) {
     MM_CUDA_TRY(cudaStreamSynchronize(stream));
     std::vector<unsigned long long> h(8 * cfg.gridDim.x);
@@ -749,10 +836,25 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
   return MM_OK;
 }
 
+// float, row-major A, single-pass TF32: A's rounding is fused into the GEMM kernel (FuseA).
+// MM_TCGEN05_FUSE_A=0 restores the separate round_tf32_kernel pass for A/B measurements.
+bool tcgen05_fuse_a(int dtype, int flags) {
+  static const bool enabled = [] {
+    const char *e = std::getenv("MM_TCGEN05_FUSE_A");
+    return !(e && e[0] == '0');
+  }();
+  return enabled && dtype == MM_DTYPE_FLOAT && !(flags & (MM_FLAG_TRANSPOSED_A | MM_FLAG_TF32X3)) &&
+         !experiment_no_round();
+}
+
 // C[rows x m] = Aop[rows x k] * B on the tensor cores; `b_op` is the K-major copy B^T (m x k), or
-// the caller's row-major B (k x m) when tcgen05_b_direct(dtype).
+// the caller's row-major B (k x m) when tcgen05_b_direct(dtype).  `a_raw` non-null: a_op is the
+// (not yet written) rounded-copy buffer and the kernel rounds `a_raw` into it itself; `counters`
+// then provides the per-granule completion counters.
 int tcgen05_gemm(int dtype, const void *a_op, const void *b_op, void *c, unsigned rows, unsigned k,
-                 unsigned m, int flags, unsigned int *tile_sync, cudaStream_t stream) {
+                 unsigned m, int flags, unsigned int *tile_sync, const void *a_raw, unsigned int *counters,
+                 cudaStream_t stream) {
+  const unsigned k_orig = k;
   if (split3(dtype, flags)) k *= 3;  // the operands carry [hi|hi|lo] x [hi|lo|hi] per 16-block of K
   const bool is_f32 = dtype == MM_DTYPE_FLOAT;
   const size_t eb = is_f32 ? 4 : 2;
@@ -765,16 +867,26 @@ int tcgen05_gemm(int dtype, const void *a_op, const void *b_op, void *c, unsigne
            : make_operand_map(&map_b, b_op, dtype, m, k, cg == 2 ? Geo<2>::LOAD_N : Geo<1>::LOAD_N);
   if (rc != MM_OK) return rc;
   const uint32_t k_bytes = uint32_t(size_t(k) * eb);
+  static const uint32_t late_warps = [] {
+    const char *e = std::getenv("MM_TCGEN05_FUSE_A_LATE_WARPS");
+    return uint32_t(std::min(std::max(e ? std::atoi(e) : 1, 1), PREP_WARPS));
+  }();
+  FuseA fuse{static_cast<const float4 *>(a_raw), static_cast<float4 *>(const_cast<void *>(a_op)), counters, k_orig,
+             late_warps};
+  if (is_f32 && a_raw != nullptr) {
+    return cg == 2 ? launch_gemm_variant<ptx::KIND_TF32, float, 2, false, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream)
+                   : launch_gemm_variant<ptx::KIND_TF32, float, 1, false, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream);
+  }
   if (is_f32) {
-    return cg == 2 ? launch_gemm_variant<ptx::KIND_TF32, float, 2, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream)
-                   : launch_gemm_variant<ptx::KIND_TF32, float, 1, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream);
+    return cg == 2 ? launch_gemm_variant<ptx::KIND_TF32, float, 2, false, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream)
+                   : launch_gemm_variant<ptx::KIND_TF32, float, 1, false, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream);
   }
   if (bmn) {
-    return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream)
-                   : launch_gemm_variant<ptx::KIND_F16, __half, 1, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream);
+    return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2, true, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream)
+                   : launch_gemm_variant<ptx::KIND_F16, __half, 1, true, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream);
   }
-  return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream)
-                 : launch_gemm_variant<ptx::KIND_F16, __half, 1, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, stream);
+  return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2, false, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream)
+                 : launch_gemm_variant<ptx::KIND_F16, __half, 1, false, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream);
 }
 
 int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_bytes) {
@@ -790,8 +902,9 @@ int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_b
     MM_CUDA_TRY(cudaFuncGetAttributes(&attr, round_tf32_kernel));
     MM_CUDA_TRY(cudaFuncGetAttributes(&attr, transpose_prep_kernel<float, true>));
     MM_CUDA_TRY(cudaFuncGetAttributes(&attr, transpose_prep_kernel<__half, false>));
-    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_TF32, float, 2, false>));
-    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_F16, __half, 2, true>));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_TF32, float, 2, false, true>));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_TF32, float, 2, false, false>));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_F16, __half, 2, true, false>));
     if (!get_encode_fn()) return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     return MM_OK;
   }
@@ -799,15 +912,16 @@ int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_b
   void *bt = sp;
   void *aprep = sp + tcgen05_bt_bytes(dtype, g.k, g.m, g.flags);
   unsigned int *tile_sync = reinterpret_cast<unsigned int *>(sp + scratch_bytes - TILE_SYNC_BYTES);
+  unsigned int *a_done = reinterpret_cast<unsigned int *>(sp + scratch_bytes - TAIL_BYTES);
 
   const void *b_op = nullptr;
   int rc = tcgen05_prepare_b(dtype, g.b, bt, g.k, g.m, g.flags, &b_op, g.stream);
   if (rc != MM_OK) return rc;
-  const void *a_op = nullptr;
-  rc = tcgen05_prepare_a(dtype, g.a, aprep, g.n, g.k, g.flags, &a_op, g.stream);
+  const void *a_op = nullptr, *a_raw = nullptr;
+  rc = tcgen05_prepare_a(dtype, g.a, aprep, g.n, g.k, g.flags, &a_op, &a_raw, g.stream);
   if (rc != MM_OK) return rc;
   if (g.ev_prep_done) MM_CUDA_TRY(cudaEventRecord(g.ev_prep_done, g.stream));
-  return tcgen05_gemm(dtype, a_op, b_op, g.c, g.n, g.k, g.m, g.flags, tile_sync, g.stream);
+  return tcgen05_gemm(dtype, a_op, b_op, g.c, g.n, g.k, g.m, g.flags, tile_sync, a_raw, a_done, g.stream);
 }
 
 }  // namespace mm

@@ -57,7 +57,9 @@ def test_static_queries(mm):
     assert mm.kernel_path(mm.FLOAT, mm.ADD, mm.MIN) == "semiring_simt"
     assert mm.kernel_path(mm.FLOAT, flags=mm.FLAG_EXACT) == "semiring_simt"
     assert mm.kernel_path(mm.INT32) == "semiring_simt"
-    assert mm.launch_count(mm.FLOAT) == 3 and mm.launch_count(mm.DOUBLE) == 1
+    # float: B^T preparation + GEMM (A's TF32 rounding is fused into the GEMM kernel), 3 with MM_TCGEN05_FUSE_A=0
+    assert mm.launch_count(mm.FLOAT) in (2, 3) and mm.launch_count(mm.DOUBLE) == 1
+    assert mm.launch_count(mm.HALF) in (1, 2)
 
 
 def _has_gpu():
