@@ -31,6 +31,7 @@
 
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include "tma_host.cuh"
 
 namespace mm {
 namespace {
@@ -547,25 +548,6 @@ split3_transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, 
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
-                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-  });
-  return fn;
-}
-
 // K-major operand: `rows` rows of `k_elems` elements, row pitch k_elems * elem_bytes;
 // box = {128 bytes of K, box_rows}, 128-byte swizzle, out-of-bounds reads return zeros
 // (neutral for (Multiply, Add) — SURVEY.md section 5 trap 3).

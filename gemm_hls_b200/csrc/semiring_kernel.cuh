@@ -15,15 +15,21 @@
 // so K % BK == 0 is implied by the reference's own shape rule), 256 threads, 8 x 8 accumulators
 // per thread laid out as 2 x 2 quads of 4 so that shared-memory fragment reads are 16-byte
 // conflict-free and global C stores are row-contiguous.  A is transposed on the way into shared
-// memory (the role of TransposeA, kernel/Memory.cpp:130-181); tiles are double buffered with the
-// next tile's global loads in flight during the current tile's compute.
+// memory (the role of TransposeA, kernel/Memory.cpp:130-181) through registers, with the next
+// tile's global loads in flight during the current tile's compute; the B tile (BK rows x 128
+// columns, natural orientation — the role of ReadB/FeedB) is staged by TMA
+// (cp.async.bulk.tensor + mbarrier complete_tx), the same mechanism the tensor-core path uses.
+// No warp-shuffle reduction is needed (or wanted): K is never split across lanes, which is what
+// keeps the reduction order — and therefore every rounding — identical to Naive<>.
 #pragma once
 
 #include <cuda_runtime.h>
 
 #include <type_traits>
 
+#include "ptx_sm100.cuh"
 #include "semiring.cuh"
+#include "tma_host.cuh"
 
 namespace mm {
 
@@ -52,7 +58,9 @@ struct SemiringTile {
   static constexpr int PAD = 4;                               // elements; keeps 16 B alignment for T >= 4 B
   static constexpr int LDA = BM + ((sizeof(T) >= 4) ? PAD : 16 / sizeof(T));
   static constexpr int LDB = BN;
-  static constexpr size_t SMEM_BYTES = 2 * (size_t(BK) * LDA + size_t(BK) * LDB) * sizeof(T);
+  static constexpr size_t A_BYTES = (2 * size_t(BK) * LDA * sizeof(T) + 127) / 128 * 128;  // keeps Bs 128-B aligned
+  static constexpr size_t B_TILE_BYTES = size_t(BK) * LDB * sizeof(T);                     // one TMA box
+  static constexpr size_t SMEM_BYTES = A_BYTES + 2 * B_TILE_BYTES + 16 /* two mbarriers */;
 };
 
 // 2 CTAs (16 warps) per SM for 4-byte element types: 64 accumulators + two k-steps of fragments fit
@@ -60,16 +68,17 @@ struct SemiringTile {
 // 2-byte types (one 32-bit register per unpacked element) spill at 128: those run 1 CTA per SM.
 template <typename T, class Map, class Reduce>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4) ? 2 : 1)
-semiring_tile_kernel(const T *__restrict__ A, const T *__restrict__ B, T *__restrict__ C,
+semiring_tile_kernel(const T *__restrict__ A, const __grid_constant__ CUtensorMap tmap_b, T *__restrict__ C,
                      unsigned size_n, unsigned size_k, unsigned size_m,
                      bool TRANSPOSED_A) {
   using Cfg = SemiringTile<T>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, VEC = Cfg::VEC;
   constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *As = reinterpret_cast<T *>(smem_raw);                 // [2][BK][LDA]  (k-major: A transposed)
-  T *Bs = As + 2 * BK * LDA;                               // [2][BK][LDB]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  T *As = reinterpret_cast<T *>(smem_raw);                          // [2][BK][LDA]  (k-major: A transposed)
+  T *Bs = reinterpret_cast<T *>(smem_raw + Cfg::A_BYTES);           // [2][BK][LDB]  (TMA destination)
+  const uint32_t bar0 = ptx::smem_u32(smem_raw + Cfg::A_BYTES + 2 * Cfg::B_TILE_BYTES);  // full[0], full[1]
 
   const int tid = threadIdx.x;
   const int tx = tid % 16;  // column quad index
@@ -85,7 +94,22 @@ semiring_tile_kernel(const T *__restrict__ A, const T *__restrict__ B, T *__rest
   }
 
   Chunk16<T> a_stage[Cfg::CHUNKS_PER_THREAD];
-  Chunk16<T> b_stage[Cfg::CHUNKS_PER_THREAD];
+
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&tmap_b);
+    ptx::mbar_init(bar0, 1);
+    ptx::mbar_init(bar0 + 8, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  // B tile kt -> Bs[buf]: one elected thread arms the barrier with the byte count and issues the TMA
+  auto load_b_tma = [&](int buf, unsigned k0) {
+    if (tid == 0) {
+      ptx::mbar_arrive_expect_tx(bar0 + 8 * buf, uint32_t(Cfg::B_TILE_BYTES));
+      ptx::tma_load_2d(ptx::smem_u32(Bs + buf * BK * LDB), &tmap_b, bar0 + 8 * buf, int32_t(col0), int32_t(k0),
+                       ptx::L2_EVICT_NORMAL);
+    }
+  };
 
   auto load_global = [&](unsigned k0) {
 #pragma unroll
@@ -109,19 +133,11 @@ semiring_tile_kernel(const T *__restrict__ A, const T *__restrict__ B, T *__rest
           a_stage[i].v[v] = A[size_t(k0 + kk) * size_n + row];
         }
       }
-      {
-        const int kk = c / Cfg::B_CHUNKS_PER_ROW;
-        const int part = c % Cfg::B_CHUNKS_PER_ROW;
-        size_t col = col0 + size_t(part) * VEC;
-        if (col + VEC > size_m) col = size_m - VEC;  // M % VEC == 0 by the shape rule
-        b_stage[i] = *reinterpret_cast<const Chunk16<T> *>(B + size_t(k0 + kk) * size_m + col);
-      }
     }
   };
 
   auto store_shared = [&](int buf) {
     T *as = As + buf * BK * LDA;
-    T *bs = Bs + buf * BK * LDB;
 #pragma unroll
     for (int i = 0; i < Cfg::CHUNKS_PER_THREAD; ++i) {
       const int c = tid + i * Cfg::THREADS;
@@ -135,22 +151,23 @@ semiring_tile_kernel(const T *__restrict__ A, const T *__restrict__ B, T *__rest
         const int part = c % Cfg::B_CHUNKS_PER_ROW;
         *reinterpret_cast<Chunk16<T> *>(as + kk * LDA + part * VEC) = a_stage[i];
       }
-      {
-        const int kk = c / Cfg::B_CHUNKS_PER_ROW;
-        const int part = c % Cfg::B_CHUNKS_PER_ROW;
-        *reinterpret_cast<Chunk16<T> *>(bs + kk * LDB + part * VEC) = b_stage[i];
-      }
     }
   };
 
   const unsigned k_tiles = size_k / BK;
+  load_b_tma(0, 0);
   load_global(0);
   store_shared(0);
   __syncthreads();
+  ptx::mbar_wait(bar0, 0);
 
   for (unsigned kt = 0; kt < k_tiles; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < k_tiles) load_global((kt + 1) * BK);
+    if (kt + 1 < k_tiles) {
+      // buffer buf^1 was last read in iteration kt-1, which ended with a __syncthreads()
+      load_b_tma(buf ^ 1, (kt + 1) * BK);
+      load_global((kt + 1) * BK);
+    }
 
     const T *as = As + buf * BK * LDA;
     const T *bs = Bs + buf * BK * LDB;
@@ -187,6 +204,8 @@ semiring_tile_kernel(const T *__restrict__ A, const T *__restrict__ B, T *__rest
 
     if (kt + 1 < k_tiles) store_shared(buf ^ 1);
     __syncthreads();
+    // tile kt+1 of B: phase parity of barrier (buf^1) = number of earlier uses of that buffer, mod 2
+    if (kt + 1 < k_tiles) ptx::mbar_wait(bar0 + 8 * (buf ^ 1), ((kt + 1) >> 1) & 1u);
   }
 
   // Write the C tile once, masked to n < N, m < M (the role of WriteC, kernel/Memory.cpp:361-392).
@@ -218,9 +237,12 @@ int launch_semiring_typed(const void *a, const void *b, void *c, unsigned n, uns
   dim3 grid((m + Cfg::BN - 1) / Cfg::BN, (n + Cfg::BM - 1) / Cfg::BM);
   dim3 block(Cfg::THREADS);
   const T *pa = static_cast<const T *>(a);
-  const T *pb = static_cast<const T *>(b);
   T *pc = static_cast<T *>(c);
-  semiring_tile_kernel<T, Map, Reduce><<<grid, block, Cfg::SMEM_BYTES, stream>>>(pa, pb, pc, n, k, m,
+  CUtensorMap tmap_b;  // B row-major K x M, box = BK rows x 128 columns
+  if (encode_plain_2d(&tmap_b, b, sizeof(T), k, m, Cfg::BK, Cfg::BN) != 0) {
+    return static_cast<int>(cudaErrorInvalidValue);
+  }
+  semiring_tile_kernel<T, Map, Reduce><<<grid, block, Cfg::SMEM_BYTES, stream>>>(pa, tmap_b, pc, n, k, m,
                                                                                 transposed_a);
   return static_cast<int>(cudaGetLastError());
 }
