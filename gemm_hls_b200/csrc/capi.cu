@@ -316,7 +316,7 @@ int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags) {
     case kPathTcgen05:
       // [B^T prep unless B is read directly] + [A prep for float or transposed A] + GEMM
       return 1 + (mm::tcgen05_b_direct(dtype) ? 0 : 1) +
-             (((dtype == MM_DTYPE_FLOAT && !mm::tcgen05_fuse_a(dtype, flags)) || (flags & MM_FLAG_TRANSPOSED_A)) ? 1 : 0);
+             ((dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) ? 1 : 0);
     case kPathDmma: return 1;
     case kPathSemiring: return 1;
   }

@@ -143,6 +143,7 @@ struct FuseA {
   unsigned int *a_done;   // one counter per granule, zeroed by the launcher; complete == gridDim.x
   uint32_t k_elems;
   uint32_t late_warps;    // rounding warps per CTA that keep working after the first raster group (1..4)
+  uint32_t pre_done;      // leading granules already rounded by a separate launch before this kernel
 };
 constexpr int PREP_WARPS = 4;
 constexpr int PREP_ROWS = 256;   // granule height = pair-tile height, so a CTA's 128 rows lie in one granule
@@ -235,7 +236,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (FUSE_A) {
           // rows [a_row, a_row + 128) lie in granule a_row / PREP_ROWS; granules complete in order
           const int32_t granule = a_row / PREP_ROWS;
-          if (granule > a_ready) {
+          if (granule > a_ready && granule >= int32_t(fuse.pre_done)) {
             // All CTAs of this persistent grid are resident (grid <= SMs, 1 CTA per SM), so the
             // rounding warps of every CTA make progress while this thread spins.  The bound only
             // turns an impossible-to-satisfy wait (e.g. a tool that serialises CTAs) into a trap.
@@ -363,7 +364,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // keep sweeping: less HBM / L2 pressure on the GEMM's own loads.  Streaming (evict-first)
     // accesses keep the sweep from displacing the A / B^T panels the co-running tiles share in L2.
     const uint32_t first_granules = RASTER_GROUP_ROWS / PREP_ROWS;
-    for (uint32_t gr = 0; gr < granules; ++gr) {
+    for (uint32_t gr = fuse.pre_done; gr < granules; ++gr) {
       const uint32_t active = (gr < first_granules) ? uint32_t(PREP_WARPS) : fuse.late_warps;
       const size_t begin = size_t(gr) * PREP_ROWS * k4;
       const size_t end = size_t(min(rows, (gr + 1) * PREP_ROWS)) * k4;
@@ -680,7 +681,15 @@ int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsi
   *a_op = a;
   *a_raw = nullptr;
   if (tcgen05_fuse_a(dtype, flags) && size_t(rows) / PREP_ROWS < A_DONE_BYTES / sizeof(unsigned int)) {
-    // the GEMM kernel rounds A into `aprep` itself
+    // The GEMM kernel rounds A into `aprep` itself, in the background.  The rows of the first
+    // raster group — what the first wave of tiles needs before it can start — are rounded here by
+    // the stand-alone kernel (25 us at 16384^3), so that the GEMM does not begin with a stall.
+    const unsigned head = std::min<unsigned>(rows, RASTER_GROUP_ROWS);
+    const size_t count4 = size_t(head) * k / 4;
+    const int blocks = int(std::min<size_t>((count4 + 255) / 256, size_t(num_sms()) * 16));
+    round_tf32_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float4 *>(a), static_cast<float4 *>(aprep),
+                                                 count4);
+    MM_CUDA_TRY(cudaGetLastError());
     *a_op = aprep;
     *a_raw = a;
     return MM_OK;
@@ -818,12 +827,15 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
   return MM_OK;
 }
 
-// float, row-major A, single-pass TF32: A's rounding is fused into the GEMM kernel (FuseA).
-// MM_TCGEN05_FUSE_A=0 restores the separate round_tf32_kernel pass for A/B measurements.
+// float, row-major A, single-pass TF32: A's rounding can be fused into the GEMM kernel (FuseA).
+// EXPERIMENTAL, off by default (MM_TCGEN05_FUSE_A=1 enables it): measured over three variants
+// (profiles/r01_exp_fuse_a*.log) the background sweep slows the power- and bandwidth-sharing GEMM by
+// about what the separate 0.34 ms pass costs (step 10.47-10.68 ms fused vs 10.37-10.80 ms separate),
+// so the simpler path without a cross-CTA wait stays the default.
 bool tcgen05_fuse_a(int dtype, int flags) {
   static const bool enabled = [] {
     const char *e = std::getenv("MM_TCGEN05_FUSE_A");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return enabled && dtype == MM_DTYPE_FLOAT && !(flags & (MM_FLAG_TRANSPOSED_A | MM_FLAG_TF32X3)) &&
          !experiment_no_round();
@@ -853,8 +865,11 @@ int tcgen05_gemm(int dtype, const void *a_op, const void *b_op, void *c, unsigne
     const char *e = std::getenv("MM_TCGEN05_FUSE_A_LATE_WARPS");
     return uint32_t(std::min(std::max(e ? std::atoi(e) : 1, 1), PREP_WARPS));
   }();
+  // leading granules covered by tcgen05_prepare_a's stand-alone pass over the first raster group
+  const unsigned head = std::min<unsigned>(rows, RASTER_GROUP_ROWS);
+  const uint32_t pre_done = (head == rows) ? (rows + PREP_ROWS - 1) / PREP_ROWS : head / PREP_ROWS;
   FuseA fuse{static_cast<const float4 *>(a_raw), static_cast<float4 *>(const_cast<void *>(a_op)), counters, k_orig,
-             late_warps};
+             late_warps, pre_done};
   if (is_f32 && a_raw != nullptr) {
     return cg == 2 ? launch_gemm_variant<ptx::KIND_TF32, float, 2, false, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream)
                    : launch_gemm_variant<ptx::KIND_TF32, float, 1, false, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream);
