@@ -1,5 +1,5 @@
 #!/bin/bash
-# Final r01 refresh after the fused A rounding: suite, float benches, launch list, ncu capture, sanitizers
+# Final r01 refresh (default configuration): suite, float benches, launch list, ncu capture, power-meter run
 set +e
 mkdir -p gpurun_out/r01
 O=gpurun_out/r01
@@ -10,7 +10,19 @@ timeout 900 python bench.py > $O/bench_float16384_default.json 2>$O/bench_float1
 timeout 900 python bench.py --steps 100 --no-e2e --no-cpu > $O/bench_float16384_sustained.json 2>/dev/null; tail -1 $O/bench_float16384_sustained.json | python -c "$J" "float16384 x100"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_float16384.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > /dev/null 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 1 -c 1 -f -o $O/ncu_tcgen05_tf32 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > /dev/null 2>&1; echo "ncu rc=$?"
-for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 5 python scripts/sanitize_small.py > $O/sanitizer_$tool.log 2>&1
-  echo "$tool rc=$?"; grep -E "SUMMARY" $O/sanitizer_$tool.log
+echo "== RunHardware with the NVML power meter"
+mkdir -p /tmp/hostbuild && cd /tmp/hostbuild && python - <<'PY'
+import re,os
+root=os.environ.get("GRAFT_REPO_ROOT","/root/repo")
+t=open(root+"/gemm_hls_b200/host/Config.h.in").read()
+cfg=dict(MM_HOST_DATA_TYPE="float",MM_DATA_TYPE="float",MM_DTYPE_CODE="MM_DTYPE_FLOAT",MM_MAP_OP_UPPER="MULTIPLY",MM_MAP_OP="Multiply",MM_REDUCE_OP_UPPER="ADD",MM_REDUCE_OP="Add",MM_MEMORY_BUS_WIDTH_K=64,MM_MEMORY_BUS_WIDTH_M=64,MM_SIZE_N=512,MM_SIZE_K=512,MM_SIZE_M=512,MM_MEMORY_TILE_SIZE_N=128,MM_MEMORY_TILE_SIZE_M=256)
+t=re.sub(r"\$\{(\w+)\}",lambda m:str(cfg[m.group(1)]),t).replace("#cmakedefine MM_EXACT","/* #undef MM_EXACT */")
+open("Config.h","w").write(t)
+PY
+R=${GRAFT_REPO_ROOT:-/root/repo}
+for exe in TestSimulation RunHardware PrintSpecifications; do
+  src=$R/gemm_hls_b200/host/$exe.cpp; extra=""; [ $exe = TestSimulation ] && extra=$R/gemm_hls_b200/host/KernelEntry.cpp
+  g++ -std=c++17 -O2 -DMM_DYNAMIC_SIZES -I. -I$R/include -I$R/gemm_hls_b200/host $src $extra -L$R/gemm_hls_b200 -lmm_b200 -Wl,-rpath,$R/gemm_hls_b200 -ldl -lpthread -o $exe || echo "build of $exe failed"
 done
+cd $R
+( /tmp/hostbuild/TestSimulation 513 528 528; echo "TestSimulation rc=$?"; /tmp/hostbuild/RunHardware 1024 1024 1024 hw on; echo "RunHardware rc=$?"; MM_POWER_METER=1 /tmp/hostbuild/RunHardware 16384 16384 16384 hw off; echo "RunHardware(power) rc=$?"; /tmp/hostbuild/PrintSpecifications 16384 16384 16384 ) > $O/host_executables.log 2>&1; grep -E "rc=|Kernel executed|verified|average power" $O/host_executables.log
