@@ -49,4 +49,18 @@ inline int encode_plain_2d(CUtensorMap *map, const void *base, size_t elem_bytes
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
 }
 
+// Same array, 8-byte elements, 128-byte-swizzled tiles of box_rows x 16 elements (one 128-byte
+// swizzle row per tile row); out-of-bounds elements read as zero.
+inline int encode_sw128_2d_f64(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 8};
+  cuuint32_t box[2] = {16, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return static_cast<int>(enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), gdim, gstride, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+}
+
 }  // namespace mm
