@@ -290,8 +290,12 @@ def main():
                          " / 2 (kind::tf32 issues at half the 16-bit rate)" if path == "tcgen05_tf32" else ""))
             roof = {"bound": "tensor", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TFLOP/s"}
         elif path == "dmma_f64":
-            peak = 37.0  # FP64 DMMA: no measured figure in MEASURED_PEAKS.json; HGX B200 datasheet 296 TF / 8 GPUs
-            peak_note = "nominal FP64 tensor (DMMA) 37 TF/s per GPU (datasheet; not in MEASURED_PEAKS.json)"
+            # FP64 DMMA is not in MEASURED_PEAKS.json.  Measured on this pool with a registers-only DMMA loop
+            # (scripts/exp_fp64_pipes.cu, profiles/r01_exp_fp64_pipes.jsonl): 37.05-37.13 TF/s at 1965 MHz
+            # = 64 FMA/clk/SM; the HGX B200 datasheet's 296 TF / 8 GPUs = 37 TF/s.
+            peak = 37.1
+            peak_note = ("FP64 tensor (DMMA) 37.1 TF/s: registers-only DMMA loop measured on this pool "
+                         "(profiles/r01_exp_fp64_pipes.jsonl); datasheet 37; not in MEASURED_PEAKS.json")
             roof = {"bound": "tensor", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TFLOP/s"}
         else:
             # derived CUDA-core issue ceiling for (add, min): 2 FADD + 1 FMNMX3 per two element-steps

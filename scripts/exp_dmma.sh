@@ -1,4 +1,5 @@
 #!/bin/bash
+# Ran against the LDGSTS-fed DMMA kernel (before commit ad15438); MM_DMMA_WARPS no longer exists.
 set +e
 mkdir -p gpurun_out
 out=gpurun_out/exp_dmma.log; : > $out

@@ -29,21 +29,19 @@ print(json.dumps({"rows": rows, "ms": t * 1e3, "tflops": 2.0 * rows * k * m / t 
 
 out = []
 for rows in (8192, 4096, 2048, 1024):
-    for setting, ws in (("128", "1"), ("64", "1"), ("auto", "1"), ("auto", "0")):
+    for setting in ("128", "64", "auto"):
         env = dict(os.environ)
         env.pop("MM_DMMA_TILE_ROWS", None)
-        env["MM_DMMA_WS"] = ws  # 1 = warp-specialised kernel (default), 0 = every warp prefetches
         if setting != "auto":
             env["MM_DMMA_TILE_ROWS"] = setting
         try:
             r = subprocess.run([sys.executable, "-c", CHILD, str(rows)], env=env, capture_output=True, text=True, timeout=120)
         except subprocess.TimeoutExpired:
-            print({"rows": rows, "tile_rows": setting, "ws": ws, "error": "timeout"}, flush=True)
+            print({"rows": rows, "tile_rows": setting, "error": "timeout"}, flush=True)
             continue
         line = [l for l in r.stdout.splitlines() if l.startswith("{")]
         d = json.loads(line[-1]) if line else {"error": r.stderr[-400:]}
         d["tile_rows"] = setting
-        d["warp_specialised"] = ws
         out.append(d)
         print(d, flush=True)
 os.makedirs("gpurun_out", exist_ok=True)

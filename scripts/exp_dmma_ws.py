@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """DMMA kernel generations on double rows x 8192 x 8192: TMA-fed (MM_DMMA_TMA=1, default), LDGSTS producer
-warps (MM_DMMA_TMA=0, MM_DMMA_PRODUCERS=1|4), every warp prefetching (MM_DMMA_WS=0)."""
+warps (MM_DMMA_TMA=0, MM_DMMA_PRODUCERS=1|4), every warp prefetching (MM_DMMA_WS=0).
+These switches exist at commit ad15438 only; afterwards the TMA-fed kernel is the only one."""
 import os
 import subprocess
 import sys

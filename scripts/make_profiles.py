@@ -58,7 +58,7 @@ def main():
         mine = {}
         for r in body:
             name = r[kn]
-            for key in ("gemm_tcgen05_kernel", "transpose_prep_kernel", "round_tf32_kernel", "gemm_dmma_kernel",
+            for key in ("gemm_tcgen05_kernel", "transpose_prep_kernel", "round_tf32_kernel", "gemm_dmma",
                         "semiring_tile_kernel", "split3"):
                 if key in name:
                     mine.setdefault(key, []).append(float(r[val].replace(",", "")))

@@ -17,6 +17,7 @@ CASES = [
     ("tcgen05_f16", G.HALF, G.MULTIPLY, G.ADD, 0, (257, 96, 288)),
     ("dmma_f64", G.DOUBLE, G.MULTIPLY, G.ADD, 0, (130, 24, 136)),
     ("dmma_f64 TA", G.DOUBLE, G.MULTIPLY, G.ADD, G.FLAG_TRANSPOSED_A, (130, 24, 136)),
+    ("dmma_f64 3 stages wrap", G.DOUBLE, G.MULTIPLY, G.ADD, 0, (70, 200, 264)),
     ("semiring f32 addmin", G.FLOAT, G.ADD, G.MIN, 0, (129, 48, 144)),
     ("semiring f32 exact", G.FLOAT, G.MULTIPLY, G.ADD, G.FLAG_EXACT, (129, 48, 144)),
     ("semiring i32", G.INT32, G.MULTIPLY, G.ADD, 0, (65, 32, 48)),
@@ -24,8 +25,11 @@ CASES = [
     ("semiring f16 exact", G.HALF, G.MULTIPLY, G.ADD, G.FLAG_EXACT, (65, 64, 96)),
     ("semiring f64 addmax TA", G.DOUBLE, G.ADD, G.MAX, G.FLAG_TRANSPOSED_A, (67, 16, 24)),
 ]
+only = os.environ.get("SANITIZE_ONLY")  # substring filter on the case name, e.g. SANITIZE_ONLY=dmma
 bad = 0
 for name, dt, mp, rd, flags, (n, k, m) in CASES:
+    if only and only not in name:
+        continue
     a, b = O.fill(dt, n, k, m, 3)
     if dt == G.HALF:
         a = (a.astype(np.float32) * np.float32(0.25)).astype(np.float16)
