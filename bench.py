@@ -213,6 +213,19 @@ def main():
         b_full = torch.empty((K, M), device=dev, dtype=t_dt)
     if world > 1:
         dist.broadcast(b_full, src=0)  # the ONE collective of the path: B over NVLink/NVSwitch
+        # reported beside the step time: the same broadcast once more, now that the
+        # communicator exists, timed on the device, max over ranks
+        torch.cuda.synchronize()
+        dist.barrier()
+        eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eb0.record()
+        dist.broadcast(b_full, src=0)
+        eb1.record()
+        torch.cuda.synchronize()
+        tb = torch.tensor([eb0.elapsed_time(eb1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        config["broadcast_b_ms"] = round(float(tb.item()), 4)
+        config["broadcast_b_bytes"] = b_full.numel() * b_full.element_size()
     c_blk = torch.empty((n_local, M), device=dev, dtype=t_dt)
     torch.cuda.synchronize()
 
