@@ -311,11 +311,20 @@ def main():
                          "(profiles/r01_exp_fp64_pipes.jsonl); datasheet 37; not in MEASURED_PEAKS.json")
             roof = {"bound": "tensor", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TFLOP/s"}
         else:
-            # derived CUDA-core issue ceiling for (add, min): 2 FADD + 1 FMNMX3 per two element-steps
-            # = 1.5 issue slots per step -> 85 steps/clk/SM -> 49.5 TOp/s at 1965 MHz
-            peak = 49.5
-            peak_note = ("derived FP32 add + 3-input min issue ceiling 49.5 TOp/s at 1965 MHz (DESIGN.md 3.3); "
-                         "neither HBM- nor tensor-bound: CUDA-core issue rate")
+            # derived CUDA-core issue ceiling: one warp instruction per clock and scheduler
+            # = 148 SMs x 4 x 32 lanes x 1.965 GHz = 37.2e12 lane-instructions/s, 2 ops per element-step.
+            #   float (Add, Min|Max): 1 FADD2 + 1 FMNMX3 per two element-steps = 1.0 slot per step -> 74.4 TOp/s
+            #     (the half-rate ALU pipe of the FMNMX3 gives the same bound); the inner loop alone, on a
+            #     resident tile, measures 44.8 TOp/s (scripts/exp_semiring_issue.cu)
+            #   anything else (e.g. float (Multiply, Add) under MM_FLAG_EXACT: 1 FMUL2 per two steps + 1 FADD
+            #     per step): 1.5 slots per step -> 49.6
+            fast_minmax = dtype_name == "float" and mp_name == "Add" and rd_name in ("Min", "Max") and not (flags & 2)
+            peak = 74.4 if fast_minmax else 49.6
+            peak_note = ("derived CUDA-core issue ceiling at 1965 MHz, %s (DESIGN.md 3.3)%s; neither HBM- nor "
+                         "tensor-bound" % ("1 FADD2 + 1 FMNMX3 per two element-steps" if fast_minmax else
+                                           "1.5 issue slots per element-step",
+                                           "; inner loop alone measured at 44.8 TOp/s (profiles/r01_exp_semiring_issue.jsonl)"
+                                           if fast_minmax else ""))
             roof = {"bound": "cuda_core_issue", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TOp/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["kernel"] = path

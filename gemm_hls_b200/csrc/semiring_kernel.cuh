@@ -192,12 +192,47 @@ semiring_tile_kernel(const T *__restrict__ A, const __grid_constant__ CUtensorMa
           bf[u][4 + q] = b1.v[q];
         }
       }
+      if constexpr (std::is_same<T, float>::value && PackedOp<Map>::value) {
+        // float Map = Sum / Product: two adjacent columns per instruction (FADD2 / FMUL2, A element
+        // broadcast); a Sum / Product Reduce is packed the same way, Min / Max reduce per element
+        // (FMNMX3 over the two k).  Per element the operations and their order are unchanged.
+        F32x2 bp[2][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[i][j] = Reduce::Apply(Reduce::Apply(acc[i][j], Map::Apply(af[0][i], bf[0][j])),
-                                    Map::Apply(af[1][i], bf[1][j]));
+          for (int p = 0; p < 4; ++p) bp[u][p] = pack_f32x2(bf[u][2 * p], bf[u][2 * p + 1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const F32x2 a0 = pack_f32x2(af[0][i], af[0][i]), a1 = pack_f32x2(af[1][i], af[1][i]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const F32x2 t0 = PackedOp<Map>::Apply2(a0, bp[0][p]), t1 = PackedOp<Map>::Apply2(a1, bp[1][p]);
+            // (Product, Sum) keeps the Reduce per element: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+            // into one FFMA2 (a single rounding, which Naive<> does not do) even under -fmad=false,
+            // but it never splits an FMUL2 to fuse its halves with scalar add.rn.f32.
+            constexpr bool contractable =
+                std::is_same<Map, Product<float>>::value && std::is_same<Reduce, Sum<float>>::value;
+            if constexpr (PackedOp<Reduce>::value && !contractable) {
+              const F32x2 r = PackedOp<Reduce>::Apply2(
+                  PackedOp<Reduce>::Apply2(pack_f32x2(acc[i][2 * p], acc[i][2 * p + 1]), t0), t1);
+              unpack_f32x2(r, acc[i][2 * p], acc[i][2 * p + 1]);
+            } else {
+              float t0l, t0h, t1l, t1h;
+              unpack_f32x2(t0, t0l, t0h);
+              unpack_f32x2(t1, t1l, t1h);
+              acc[i][2 * p] = Reduce::Apply(Reduce::Apply(acc[i][2 * p], t0l), t1l);
+              acc[i][2 * p + 1] = Reduce::Apply(Reduce::Apply(acc[i][2 * p + 1], t0h), t1h);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[i][j] = Reduce::Apply(Reduce::Apply(acc[i][j], Map::Apply(af[0][i], bf[0][j])),
+                                      Map::Apply(af[1][i], bf[1][j]));
+          }
         }
       }
     }
