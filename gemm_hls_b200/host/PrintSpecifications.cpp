@@ -7,6 +7,7 @@
 // evaluated twice: with the CTA tile (bytes through L2) and with the patch of C that the
 // co-running tiles share through L2 (bytes from HBM; profiles/r01_tile_sweep_half32768.csv).
 #include <algorithm>
+#include <cmath>
 #include <iomanip>
 #include <string>
 
@@ -20,11 +21,21 @@ struct KernelModel {
   unsigned tile_rows, tile_cols, sms_per_tile;
 };
 
-KernelModel ModelFor(std::string const &family) {
+KernelModel ModelFor(std::string const &family, mmhost::Shape const &s) {
   if (family == "tcgen05_f16") return {family, 2.0 * 4096, 256, 256, 2};   // UMMA 256x256x16 per 128 clk, CTA pair
   if (family == "tcgen05_tf32") return {family, 2.0 * 2048, 256, 256, 2};  // UMMA 256x256x8  per 128 clk, CTA pair
-  if (family == "dmma_f64") return {family, 2.0 * 64, 128, 128, 1};        // DMMA: 64 FMA / clk / SM
-  return {family, 2.0 * 85, 128, 128, 1};  // CUDA cores: 1.5 issue slots per element-step
+  if (family == "dmma_f64") {
+    // DMMA: 64 FMA / clk / SM; 128-row tiles, or 64-row tiles when those fill the last wave better
+    // (the launcher's rule, csrc/gemm_dmma.cu: the half-height tile has to win by more than 5 %)
+    const double cols = (s.m + 127) / 128;
+    const double full = std::ceil(((s.n + 127) / 128) * cols / 148.0), half = 0.5 * 1.05 * std::ceil(((s.n + 63) / 64) * cols / 148.0);
+    return {family, 2.0 * 64, half < full ? 64u : 128u, 128, 1};
+  }
+  // CUDA cores, one warp instruction per scheduler and clock: float (Add, Min|Max) issues
+  // 1 FADD2 + 1 FMNMX3 per two element-steps (128 steps/clk/SM), everything else is modelled at 1.5 slots
+  const bool packed_minmax = kDataTypeCode == MM_DTYPE_FLOAT && kMapOpCode == MM_OP_ADD &&
+                             (kReduceOpCode == MM_OP_MIN || kReduceOpCode == MM_OP_MAX) && !(kKernelFlags & MM_FLAG_EXACT);
+  return {family, 2.0 * (packed_minmax ? 128 : 85), 128, 128, 1};
 }
 
 template <typename T>
@@ -49,7 +60,7 @@ int main(int argc, char **argv) {
   const double mhz = next < argc ? std::stod(argv[next]) : 1965.0;  // B200 clocks.max.sm
   constexpr unsigned kSMs = 148;
 
-  const KernelModel model = ModelFor(mm_kernel_path(kDataTypeCode, kMapOpCode, kReduceOpCode, kKernelFlags));
+  const KernelModel model = ModelFor(mm_kernel_path(kDataTypeCode, kMapOpCode, kReduceOpCode, kKernelFlags), s);
   const double ops = 2.0 * s.n * static_cast<double>(s.k) * s.m;
   const double peak_gops = 1e-3 * model.ops_per_sm_clock * kSMs * mhz;
   const unsigned long tiles_n = (s.n + model.tile_rows - 1) / model.tile_rows;
