@@ -13,9 +13,14 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp, *cfg):
+def _build(tmp, *cfg, static_sizes=None):
     out = str(tmp)
-    r = subprocess.run(["bash", os.path.join(ROOT, "scripts", "build_host.sh"), out, *cfg], capture_output=True, text=True)
+    env = dict(os.environ)
+    env.pop("MM_STATIC_SIZES", None)
+    if static_sizes:
+        env["MM_STATIC_SIZES"] = static_sizes
+    r = subprocess.run(["bash", os.path.join(ROOT, "scripts", "build_host.sh"), out, *cfg], capture_output=True, text=True,
+                       env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     return out
 
@@ -75,6 +80,16 @@ def test_semiring_configuration_reports_the_cuda_core_family(mm, tmp_path):
     text = _run(os.path.join(out, "PrintSpecifications"), 8192, 8192, 8192).stdout
     assert "float (Add, Min)" in text and "semiring_simt" in text
     assert _field(text, "Ideal performance:") == pytest.approx(148 * 256 * 1965e-3, rel=1e-4)
+
+
+def test_static_size_build_takes_no_shape_arguments(mm, tmp_path):
+    """MM_DYNAMIC_SIZES=OFF (CMakeLists.txt:16,43-46 of the reference): N, K, M are compile-time constants."""
+    out = _build(tmp_path, static_sizes="1024 2048 512")
+    r = _run(os.path.join(out, "PrintSpecifications"))
+    assert r.returncode == 0
+    assert _field(r.stdout, "Number of operations:") == pytest.approx(2.0 * 1024 * 2048 * 512, rel=1e-5)
+    r = _run(os.path.join(out, "PrintSpecifications"), 64, 64, 64)
+    assert r.returncode == 1 and "Usage:" in r.stderr and "N K M" not in r.stderr
 
 
 def test_compute_without_a_gpu_fails_like_a_runtime_error(host_float):
