@@ -105,20 +105,43 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, k, m):
-    """Time the reference's own Naive<> (oracle/_ref) on `rows` rows of C; returns (seconds, kind)."""
-    import numpy as np
+def host_threads():
+    """Host threads this process may use (the affinity mask where the platform has one)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
+
+
+def reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, k, m, threads=1):
+    """Time the reference's own Naive<> (oracle/_ref) on the rows of C that `a_rows` selects.
+
+    Naive<> is single-threaded as written (include/Utility.h:18-42); C rows are independent, so
+    `threads` host threads each run the reference's unmodified routine on their own share of the rows
+    (ctypes releases the GIL during the call).  Returns (wall seconds, kind, threads used)."""
+    from concurrent.futures import ThreadPoolExecutor
     import oracle as O
     dt = {"float": O.FLOAT, "half": O.HALF, "double": O.DOUBLE}[dtype_name]
     mp, rd = getattr(O, mp_name.upper()), getattr(O, rd_name.upper())
     rows = a_rows.shape[0]
-    if O.ref_available(dt, mp, rd):
-        t0 = time.perf_counter()
-        O.ref_naive(dt, mp, rd, a_rows, b, rows, k, m)
-        return time.perf_counter() - t0, "reference"
+    threads = max(1, min(threads, rows))
+    bounds = [rows * i // threads for i in range(threads + 1)]
+    use_ref = O.ref_available(dt, mp, rd)
+
+    def work(i):
+        lo, hi = bounds[i], bounds[i + 1]
+        if use_ref:
+            O.ref_naive(dt, mp, rd, a_rows[lo:hi], b, hi - lo, k, m)
+        else:
+            O.naive(dt, mp, rd, a_rows[lo:hi], b, hi - lo, k, m, threads=1)
+
     t0 = time.perf_counter()
-    O.naive(dt, mp, rd, a_rows, b, rows, k, m, threads=1)
-    return time.perf_counter() - t0, "port"
+    if threads == 1:
+        work(0)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(work, range(threads)))
+    return time.perf_counter() - t0, ("reference" if use_ref else "port"), threads
 
 
 def main():
@@ -153,27 +176,35 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        rows_per_step = 2
+        # one step = one row of C per host thread (C rows are independent; every thread runs the
+        # reference's single-threaded Naive<> on its own row): ~5 s of wall clock at 16384^2 per row
+        threads = host_threads()
+        rows_per_step = threads
         rng = np.random.default_rng(5)
         b = rng.uniform(1, 10, size=(K, M)).astype(np_dt)
         a_rows = rng.uniform(1, 10, size=(rows_per_step, K)).astype(np_dt)
         kind = "reference"
-        for _ in range(min(args.warmup, 1)):
-            reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, K, M)
+        # one untimed step; if the host is slower than expected, shrink the per-step sample (fewer rows,
+        # fewer threads) so that K timed steps stay within a few minutes
+        t_warm, _, _ = reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, K, M, threads)
+        if t_warm > 8.0:
+            threads = max(1, int(threads * 8.0 / t_warm))
+            rows_per_step = threads
+            a_rows = a_rows[:rows_per_step]
         t = 0.0
         for _ in range(args.steps):
-            dt_s, kind = reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, K, M)
+            dt_s, kind, threads = reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, K, M, threads)
             t += dt_s
         sample_ops = 2.0 * rows_per_step * K * M
         value = 1e-9 * sample_ops * args.steps / t
-        sample = "%d rows of C per step (%d x %d x %d), Naive<> single-threaded as the reference is written" % (
-            rows_per_step, rows_per_step, K, M)
+        sample = ("%d rows of C per step (%d x %d x %d): the reference's Naive<> (single-threaded as written) on one "
+                  "row per host thread, %d threads" % (rows_per_step, rows_per_step, K, M, threads))
         print(json.dumps({
             "impl": "reference", "metric": metric_name, "value": value, "unit": metric, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_name,
             "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": value, "unit": metric, "cores": 1, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": metric, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": metric, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return 0
@@ -380,15 +411,18 @@ def main():
 
     # ------------------------------------------------------------------ cpu_baseline (rank 0, N == 1)
     if out is not None and world == 1 and not args.no_cpu:
-        sample_rows = 6 if K * M >= (8192 * 8192) else max(6, int(3e9 / (2.0 * K * M)))
+        # bounded sample: one row of C per host thread (two when that is still under ~3e9 operations in total)
+        threads = host_threads()
+        sample_rows = threads * (2 if 2.0 * 2 * threads * K * M <= 3e9 else 1)
         sample_rows = min(sample_rows, n_local)
         b_cpu = b_full.cpu().numpy()
         a_cpu = a_blk[:sample_rows].cpu().numpy()
-        secs, kind = reference_naive_sample(dtype_name, mp_name, rd_name, a_cpu, b_cpu, K, M)
-        out["cpu_baseline"] = {"value": 1e-9 * 2.0 * sample_rows * K * M / secs, "unit": metric, "cores": 1,
+        secs, kind, threads = reference_naive_sample(dtype_name, mp_name, rd_name, a_cpu, b_cpu, K, M, threads)
+        out["cpu_baseline"] = {"value": 1e-9 * 2.0 * sample_rows * K * M / secs, "unit": metric, "cores": threads,
                                "kind": kind, "seconds": secs, "host_cpus": os.cpu_count(),
-                               "sample": "first %d rows of C (%d x %d x %d) with the reference's Naive<> "
-                                         "(include/Utility.h:18-42), single thread as written" % (sample_rows, sample_rows, K, M)}
+                               "sample": "first %d rows of C (%d x %d x %d): the reference's Naive<> "
+                                         "(include/Utility.h:18-42, single-threaded as written) on %d host threads, "
+                                         "each on its own rows" % (sample_rows, sample_rows, K, M, threads)}
 
     if out is not None:
         print(json.dumps(out))

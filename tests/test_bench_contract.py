@@ -1,0 +1,53 @@
+"""bench.py's driver contract, as far as it can be exercised without a GPU: the reference arm
+(`--impl reference`: the reference's own Naive<> on the host cores) prints one JSON line with the agreed
+keys, non-zero ranks of a torchrun launch stay silent, and the B200 arm refuses to run without a device
+(no CPU fallback on the product path)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          timeout=600, env=e, cwd=ROOT)
+
+
+def test_reference_arm_line(oracle):
+    r = _bench("--impl", "reference", "--workload", "float4096", "--steps", "2", "--warmup", "1")
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3
+    assert d["unit"] == "GFLOP/s" and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["metric"].startswith("GFLOP/s at N=4096 K=4096 M=4096 float")
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert "Naive<>" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # value = sampled operations / time: rows_per_step x K x M x 2 per step
+    rows = int(cb["sample"].split()[0])
+    assert d["value"] == pytest.approx(1e-9 * 2.0 * rows * 4096 * 4096 / (1e-3 * d["ms_per_step"]), rel=1e-6)
+
+
+def test_reference_arm_runs_on_rank_zero_only(oracle):
+    r = _bench("--impl", "reference", "--workload", "float4096", "--steps", "1", "--gpus", "2",
+               env={"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_b200_arm_has_no_cpu_fallback(mm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = _bench("--workload", "float4096", "--steps", "1")
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr + r.stdout
