@@ -106,11 +106,32 @@ class ClockSampler:
 
 
 def host_threads():
-    """Host threads this process may use (the affinity mask where the platform has one)."""
+    """Host threads for the reference's CPU path: one per PHYSICAL core this process may run on.
+
+    Naive<> walks a column of B with a stride of M elements: 16384 cache lines (1 MiB) per output element,
+    reused by the next 15 columns.  That working set fits one core's private L2 once, not twice, so two
+    hyper-threads on a core evict each other (on the 128-thread host of the B200 boxes a float 16384^2 step
+    with one row on each of the 128 logical CPUs did not finish within 45 s; one row on one thread takes 5 s)."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        allowed = set(os.sched_getaffinity(0))
     except (AttributeError, OSError):
-        return max(1, os.cpu_count() or 1)
+        allowed = None
+    cores, cpu, pkg = set(), None, None
+    try:
+        for line in open("/proc/cpuinfo"):
+            key, _, val = line.partition(":")
+            key, val = key.strip(), val.strip()
+            if key == "processor":
+                cpu, pkg = int(val), None
+            elif key == "physical id":
+                pkg = val
+            elif key == "core id" and cpu is not None and (allowed is None or cpu in allowed):
+                cores.add((pkg, val))
+    except OSError:
+        pass
+    if cores:
+        return len(cores)
+    return max(1, len(allowed) if allowed else (os.cpu_count() or 1))
 
 
 def reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, k, m, threads=1):
