@@ -165,6 +165,21 @@ def reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, k, m, thread
     return time.perf_counter() - t0, ("reference" if use_ref else "port"), threads
 
 
+def cpu_baseline_line(dtype_name, mp_name, rd_name, unit, k, m, a_rows_of, b):
+    """The `cpu_baseline` object of the B200 arm: the reference's Naive<> on a bounded sample of the same
+    workload — one row of C per host thread (two when that still stays under ~3e9 operations in total).
+    `a_rows_of(rows)` returns the first rows of A as a host array (at most `rows`), `b` is B on the host."""
+    threads = host_threads()
+    a_rows = a_rows_of(threads * (2 if 2.0 * 2 * threads * k * m <= 3e9 else 1))
+    sample_rows = a_rows.shape[0]
+    secs, kind, threads = reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, k, m, threads)
+    return {"value": 1e-9 * 2.0 * sample_rows * k * m / secs, "unit": unit, "cores": threads, "kind": kind,
+            "seconds": secs, "host_cpus": os.cpu_count(),
+            "sample": "first %d rows of C (%d x %d x %d): the reference's Naive<> (include/Utility.h:18-42, "
+                      "single-threaded as written) on %d host threads, each on its own rows"
+                      % (sample_rows, sample_rows, k, m, threads)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -432,18 +447,9 @@ def main():
 
     # ------------------------------------------------------------------ cpu_baseline (rank 0, N == 1)
     if out is not None and world == 1 and not args.no_cpu:
-        # bounded sample: one row of C per host thread (two when that is still under ~3e9 operations in total)
-        threads = host_threads()
-        sample_rows = threads * (2 if 2.0 * 2 * threads * K * M <= 3e9 else 1)
-        sample_rows = min(sample_rows, n_local)
-        b_cpu = b_full.cpu().numpy()
-        a_cpu = a_blk[:sample_rows].cpu().numpy()
-        secs, kind, threads = reference_naive_sample(dtype_name, mp_name, rd_name, a_cpu, b_cpu, K, M, threads)
-        out["cpu_baseline"] = {"value": 1e-9 * 2.0 * sample_rows * K * M / secs, "unit": metric, "cores": threads,
-                               "kind": kind, "seconds": secs, "host_cpus": os.cpu_count(),
-                               "sample": "first %d rows of C (%d x %d x %d): the reference's Naive<> "
-                                         "(include/Utility.h:18-42, single-threaded as written) on %d host threads, "
-                                         "each on its own rows" % (sample_rows, sample_rows, K, M, threads)}
+        out["cpu_baseline"] = cpu_baseline_line(dtype_name, mp_name, rd_name, metric, K, M,
+                                                lambda rows: a_blk[:min(rows, n_local)].cpu().numpy(),
+                                                b_full.cpu().numpy())
 
     if out is not None:
         print(json.dumps(out))

@@ -51,3 +51,27 @@ def test_b200_arm_has_no_cpu_fallback(mm):
     r = _bench("--workload", "float4096", "--steps", "1")
     assert r.returncode != 0
     assert "no CPU fallback" in r.stderr + r.stdout
+
+
+def test_cpu_baseline_object_of_the_b200_arm(oracle):
+    """The helper the B200 arm calls with host copies of its device inputs (no GPU needed to run it)."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    k = m = 512
+    rng = np.random.default_rng(1)
+    a = rng.uniform(1, 10, size=(64, k)).astype(np.float32)
+    b = rng.uniform(1, 10, size=(k, m)).astype(np.float32)
+    asked = []
+
+    def a_rows_of(rows):
+        asked.append(rows)
+        return a[:min(rows, a.shape[0])]
+
+    cb = bench.cpu_baseline_line("float", "Multiply", "Add", "GFLOP/s", k, m, a_rows_of, b)
+    threads = bench.host_threads()
+    assert asked == [2 * threads]                     # small problem: two rows per thread
+    rows = min(2 * threads, 64)
+    assert cb["cores"] == min(threads, rows) and cb["kind"] in ("reference", "port") and cb["unit"] == "GFLOP/s"
+    assert cb["value"] == pytest.approx(1e-9 * 2.0 * rows * k * m / cb["seconds"], rel=1e-9)
+    assert cb["sample"].startswith("first %d rows of C" % rows)
