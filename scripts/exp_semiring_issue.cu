@@ -8,6 +8,9 @@
 //   variant 3: packed adds (add.rn.f32x2 -> FADD2, two adjacent columns per instruction): 1 FADD2 + 1 FMNMX3
 //              per two element-steps (1.0 issue slot per element-step; ceiling 74.4 TOp/s)
 //   variant 4: variant 3 with the column pair as the outer loop (sensitivity to instruction order)
+//   variant 5: variant 3 with the B pair of the second k swapped (free: FADD2 takes an .F32x2.LO_HI operand),
+//              so that the two sums an FMNMX3 reduces sit in registers of opposite parity (in variant 3 all
+//              three FMNMX3 sources have the same parity: candidates for register-bank conflicts)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/_build/exp_semiring_issue scripts/exp_semiring_issue.cu
 #include <cuda_runtime.h>
 
@@ -73,15 +76,20 @@ __global__ void __launch_bounds__(256, 2) loop_kernel(float *out, int k_tiles) {
 #pragma unroll
         for (int u = 0; u < 2; ++u)
 #pragma unroll
-          for (int p = 0; p < 4; ++p) bp[u][p] = pack2(bf[u][2 * p], bf[u][2 * p + 1]);
+          for (int p = 0; p < 4; ++p)
+            bp[u][p] = (VARIANT == 5 && u == 1) ? pack2(bf[u][2 * p + 1], bf[u][2 * p]) : pack2(bf[u][2 * p], bf[u][2 * p + 1]);
 #pragma unroll
         for (int x = 0; x < 8; ++x)
 #pragma unroll
           for (int y = 0; y < 4; ++y) {
-            const int i = VARIANT == 3 ? x : (y * 2 + x / 4) % 8, p = VARIANT == 3 ? y : x % 4;
+            const int i = VARIANT != 4 ? x : (y * 2 + x / 4) % 8, p = VARIANT != 4 ? y : x % 4;
             float t0l, t0h, t1l, t1h;
             add2(pack2(af[0][i], af[0][i]), bp[0][p], t0l, t0h);
-            add2(pack2(af[1][i], af[1][i]), bp[1][p], t1l, t1h);
+            if (VARIANT == 5) {
+              add2(pack2(af[1][i], af[1][i]), bp[1][p], t1h, t1l);  // swapped pair: .x is column 2p+1
+            } else {
+              add2(pack2(af[1][i], af[1][i]), bp[1][p], t1l, t1h);
+            }
             acc[i][2 * p] = fminf(fminf(acc[i][2 * p], t0l), t1l);
             acc[i][2 * p + 1] = fminf(fminf(acc[i][2 * p + 1], t0h), t1h);
           }
@@ -142,8 +150,9 @@ int main() {
   run<2>("lds128_fragments_barrier_per_ktile");
   run<3>("packed_fadd2");
   run<4>("packed_fadd2_column_pair_outer");
+  run<5>("packed_fadd2_second_k_swapped");
   run<1>("lds128_fragments");
   run<3>("packed_fadd2");
-  run<4>("packed_fadd2_column_pair_outer");
+  run<5>("packed_fadd2_second_k_swapped");
   return 0;
 }
