@@ -61,7 +61,7 @@ class PowerMeter {
   double AveragePower() const {
     double sum = 0;
     for (auto const &s : samples_) sum += s.second;
-    return samples_.empty() ? 0.0 : sum / samples_.size();
+    return samples_.empty() ? 0.0 : sum / static_cast<double>(samples_.size());
   }
 
  private:

@@ -69,7 +69,7 @@ int main(int argc, char **argv) {
   const unsigned long waves = (tiles_n * tiles_m + slots - 1) / slots;
   const double tile_seconds =
       2.0 * model.tile_rows * model.tile_cols * s.k / (model.ops_per_sm_clock * model.sms_per_tile * 1e6 * mhz);
-  const double ideal = 1e-9 * ops / peak_gops, expected = waves * tile_seconds;
+  const double ideal = 1e-9 * ops / peak_gops, expected = static_cast<double>(waves) * tile_seconds;
 
   Row("Configuration:", std::string(kDataTypeName) + " (" + kMapOpName + ", " + kReduceOpName + ")");
   Row("Kernel family:", model.family);
@@ -90,7 +90,7 @@ int main(int argc, char **argv) {
   const double through_l2 = volume(model.tile_rows, model.tile_cols);
   // patch shared through L2: 2048 rows (rasterisation group) x the columns the other tiles cover
   const double patch_rows = std::min<double>(2048, s.n);
-  const double patch_cols = std::min<double>(s.m, std::max<double>(model.tile_cols, slots * model.tile_rows / patch_rows * model.tile_cols));
+  const double patch_cols = std::min<double>(s.m, std::max<double>(model.tile_cols, static_cast<double>(slots) * model.tile_rows / patch_rows * model.tile_cols));
   const double from_hbm = volume(patch_rows, patch_cols);
   Row("Communication volume:", through_l2, " elements through L2 (CTA tile)");
   Row("", 1e-9 * through_l2 * sizeof(Data_t), " GB");
