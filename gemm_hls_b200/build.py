@@ -53,9 +53,17 @@ def compile_one(job, force, verbose, hdr_time):
     return o, True
 
 
+def newest_source():
+    return max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
 def build(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
     hdr_time = newest_header()
+    # An up-to-date library needs nothing, even where the objects it was linked from were left behind
+    # (.gpurunignore keeps gemm_hls_b200/build/ off the GPU box).
+    if not force and not verbose and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(hdr_time, newest_source()):
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
     with ThreadPoolExecutor(max_workers=max(1, (os.cpu_count() or 2))) as ex:
         jobs = [("semiring_inst.cu", "semiring_%s_%d.o" % (suffix, mp),
                  ["-DMM_INST_T=" + ctype, "-DMM_INST_MAP=%d" % mp])
