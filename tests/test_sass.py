@@ -21,7 +21,7 @@ def _functions(obj):
     path = os.path.join(OBJ, obj)
     if not os.path.exists(path):
         from gemm_hls_b200 import build as product_build
-        product_build.build()
+        product_build.build(force=True)   # the library may be current while its objects were left behind
     text = subprocess.run([CUOBJDUMP, "-sass", path], capture_output=True, text=True, check=True).stdout
     funcs, name = {}, None
     for line in text.splitlines():
