@@ -148,6 +148,10 @@ def reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, k, m, thread
     threads = max(1, min(threads, rows))
     bounds = [rows * i // threads for i in range(threads + 1)]
     use_ref = O.ref_available(dt, mp, rd)
+    if use_ref:
+        O.ref_lib(dt, mp, rd)   # load once, before the threads race for it
+    else:
+        O.lib()
 
     def work(i):
         lo, hi = bounds[i], bounds[i + 1]
