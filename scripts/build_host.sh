@@ -4,7 +4,8 @@
 #   usage: bash scripts/build_host.sh [outdir] [float|double|half|int|...] [Multiply|Add|...] [Add|Min|...]
 #   MM_STATIC_SIZES="N K M" in the environment builds the MM_DYNAMIC_SIZES=OFF flavour (sizes fixed at
 #   compile time, executables take no N K M arguments), as the reference's CMake option does.
-# RunHardware gets the NCCL multi-GPU driver (MM_NUM_GPUS) when the system nccl.h / libnccl are present.
+# RunHardware gets the NCCL multi-GPU driver (MM_NUM_GPUS) when the system nccl.h / libnccl are present
+# (MM_HOST_NO_NCCL=1 builds the plain single-GPU program).
 set -e
 R=${GRAFT_REPO_ROOT:-$(cd "$(dirname "$0")/.." && pwd)}
 OUT=${1:-/tmp/hostbuild}; TYPE=${2:-float}; MAP=${3:-Multiply}; RED=${4:-Add}
@@ -32,7 +33,7 @@ DYN="-DMM_DYNAMIC_SIZES"; [ -n "$MM_STATIC_SIZES" ] && DYN=""
 COMMON="-std=c++17 -O2 $DYN -I. -I$R/include -I$R/gemm_hls_b200/host -L$R/gemm_hls_b200 -lmm_b200 -Wl,-rpath,$R/gemm_hls_b200 -ldl -lpthread"
 g++ $R/gemm_hls_b200/host/TestSimulation.cpp $R/gemm_hls_b200/host/KernelEntry.cpp $COMMON -o TestSimulation
 g++ $R/gemm_hls_b200/host/PrintSpecifications.cpp $COMMON -o PrintSpecifications
-if [ -f /usr/include/nccl.h ] && [ -f /usr/local/cuda/include/cuda_runtime.h ]; then
+if [ -z "$MM_HOST_NO_NCCL" ] && [ -f /usr/include/nccl.h ] && [ -f /usr/local/cuda/include/cuda_runtime.h ]; then
   g++ $R/gemm_hls_b200/host/RunHardware.cpp -DMM_HAS_NCCL -I/usr/local/cuda/include $COMMON -L/usr/local/cuda/lib64 -lcudart -lnccl -o RunHardware \
     || g++ $R/gemm_hls_b200/host/RunHardware.cpp $COMMON -o RunHardware
 else
