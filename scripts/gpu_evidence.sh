@@ -67,8 +67,8 @@ if has cpu; then
   echo "== reference CPU path on this host"; timeout 900 python scripts/cpu_baseline.py 2>/dev/null | tail -1 > $O/cpu_baseline.json; head -c 400 $O/cpu_baseline.json; echo
 fi
 if has host; then
-  echo "== host executables (scripts/build_host.sh)"
-  bash scripts/build_host.sh /tmp/hostbuild > /dev/null 2>&1 || echo "host build failed"
+  echo "== host executables (scripts/build_host.sh, single-GPU programs)"
+  MM_HOST_NO_NCCL=1 bash scripts/build_host.sh /tmp/hostbuild > /dev/null 2>&1 || echo "host build failed"
   ( /tmp/hostbuild/TestSimulation 513 528 528; echo "TestSimulation rc=$?"
     /tmp/hostbuild/RunHardware 1024 1024 1024 hw on; echo "RunHardware rc=$?"
     MM_POWER_METER=1 /tmp/hostbuild/RunHardware 16384 16384 16384 hw off; echo "RunHardware(power meter) rc=$?"
