@@ -50,59 +50,81 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, board power and clock-event (throttle) reasons DURING the timed region, sampled in-process
+    through NVML every ~2 ms (nvidia-smi -lms 200 gave 2-3 samples over a 0.2 s region); falls back to
+    polling nvidia-smi when the NVML binding is missing."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, device_index):
-        self.idx = device_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, device_index, interval_s=0.002):
+        self.idx, self.interval = device_index, interval_s
+        self.samples, self.stop_flag, self.thread, self.nvml = [], threading.Event(), None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.idx
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[self.idx])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self.nvml = None
+        self.thread = threading.Thread(target=self._pump_nvml if self.nvml else self._pump_smi, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smmax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 9:
-                continue
+    def _pump_nvml(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(f[1])); smmax.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        # keep the samples taken under load (power above the idle floor) when there are any
-        loaded = [s for s, p in zip(sm, power) if p > 300.0] or sm
-        loaded_power = [p for p in power if p > 300.0]
-        return {"sm_mhz": statistics.median(loaded) if loaded else None,
-                "sm_max_mhz": max(smmax) if smmax else None,
-                "power_w_max": max(power) if power else None,
-                "power_w_avg_under_load": (sum(loaded_power) / len(loaded_power)) if loaded_power else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.perf_counter(), float(sm), float(self.max_sm), pw, int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.interval)
+
+    def _pump_smi(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active"
+        while not self.stop_flag.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in r.stdout.strip().split(",")]
+                self.samples.append((time.perf_counter(), float(f[0]), float(f[1]), float(f[2]), int(f[3], 16)))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t_begin=None, t_end=None):
+        """Summary over the samples taken in [t_begin, t_end] (the timed region; all samples when not given)."""
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=5)
+        sel = [x for x in self.samples if (t_begin is None or x[0] >= t_begin) and (t_end is None or x[0] <= t_end)]
+        if not sel:
+            sel = self.samples
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "samples": 0}
+        sm = [x[1] for x in sel]
+        power = [x[3] for x in sel]
+        bits = 0
+        for x in sel:
+            bits |= x[4]
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": max(x[2] for x in sel),
+                "power_w_max": max(power), "power_w_avg_under_load": sum(power) / len(power),
+                "samples": len(sel), "source": "nvml" if self.nvml else "nvidia-smi",
+                "reasons": sorted(k for k, v in self.REASONS.items() if bits & v)}
 
 
 def host_threads():
@@ -169,19 +191,39 @@ def reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, k, m, thread
     return time.perf_counter() - t0, ("reference" if use_ref else "port"), threads
 
 
+SAMPLE_COLS = 2048   # columns of C per sampled row of the CPU arm (full K): bounds a step to a few seconds
+
+
+def cpu_sample_inputs(np_dt, k, m, rows, rng=None, a_rows=None, b=None):
+    """The bounded sample both CPU legs time: `rows` rows of C restricted to the first SAMPLE_COLS columns, full K.
+    Fixed shape (no adaptive shrinking), so that two runs on the same box time the same work."""
+    import numpy as np
+    cols = min(SAMPLE_COLS, m)
+    if b is None:
+        b = rng.uniform(1, 10, size=(k, cols)).astype(np_dt)
+    else:
+        b = np.ascontiguousarray(b[:, :cols])
+    if a_rows is None:
+        a_rows = rng.uniform(1, 10, size=(rows, k)).astype(np_dt)
+    return a_rows, b, cols
+
+
+def cpu_sample_text(rows, k, cols, threads):
+    return ("%d rows x first %d columns of C, full K (%d x %d x %d per step): the reference's Naive<> "
+            "(include/Utility.h:18-42, single-threaded as written) on %d host threads (one per physical core), each "
+            "on its own rows; fixed sample, no adaptive shrinking" % (rows, cols, rows, k, cols, threads))
+
+
 def cpu_baseline_line(dtype_name, mp_name, rd_name, unit, k, m, a_rows_of, b):
-    """The `cpu_baseline` object of the B200 arm: the reference's Naive<> on a bounded sample of the same
-    workload — one row of C per host thread (two when that still stays under ~3e9 operations in total).
-    `a_rows_of(rows)` returns the first rows of A as a host array (at most `rows`), `b` is B on the host."""
+    """The `cpu_baseline` object of the B200 arm: the reference's Naive<> on the same bounded sample the
+    reference arm times — one row of C per physical core, first SAMPLE_COLS columns, full K."""
     threads = host_threads()
-    a_rows = a_rows_of(threads * (2 if 2.0 * 2 * threads * k * m <= 3e9 else 1))
-    sample_rows = a_rows.shape[0]
-    secs, kind, threads = reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, k, m, threads)
-    return {"value": 1e-9 * 2.0 * sample_rows * k * m / secs, "unit": unit, "cores": threads, "kind": kind,
-            "seconds": secs, "host_cpus": os.cpu_count(),
-            "sample": "first %d rows of C (%d x %d x %d): the reference's Naive<> (include/Utility.h:18-42, "
-                      "single-threaded as written) on %d host threads, each on its own rows"
-                      % (sample_rows, sample_rows, k, m, threads)}
+    a_rows, b_s, cols = cpu_sample_inputs(None, k, m, threads, a_rows=a_rows_of(threads), b=b)
+    rows = a_rows.shape[0]
+    reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b_s, k, cols, threads)  # warm-up (page faults, library load)
+    secs, kind, threads = reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b_s, k, cols, threads)
+    return {"value": 1e-9 * 2.0 * rows * k * cols / secs, "unit": unit, "cores": threads, "kind": kind,
+            "seconds": secs, "host_cpus": os.cpu_count(), "sample": cpu_sample_text(rows, k, cols, threads)}
 
 
 def main():
@@ -194,6 +236,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="MM_FLAG_* bits (debugging)")
+    ap.add_argument("--tune", default="", help="comma-separated knob=value pairs for mm_context_set_tuning (sweeps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -204,8 +247,9 @@ def main():
     ops_total = 2.0 * N * K * M
     metric = "GFLOP/s" if (mp_name, rd_name) == ("Multiply", "Add") else "GOp/s"
     metric_name = "%s at N=%d K=%d M=%d %s (%s,%s)" % (metric, N, K, M, dtype_name, mp_name, rd_name)
+    # `config` names the workload and nothing run-dependent: both arms print it byte for byte
     config = {"workload": "%s %dx%dx%d (%s,%s)" % (dtype_name, N, K, M, mp_name, rd_name), "baseline_config": cfg_label,
-              "partition": "C row-blocks over %d GPU(s), B replicated (one NCCL broadcast before timing)" % world,
+              "partition": "C row-blocks over %d GPU(s), B replicated" % args.gpus,
               "l2": "inputs (A+B+C = %.2f GB) far larger than the 126 MB L2; no explicit flush" %
                     (1e-9 * {"float": 4, "half": 2, "double": 8}[dtype_name] * (N * K + K * M + N * M))}
 
@@ -216,35 +260,27 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # one step = one row of C per host thread (C rows are independent; every thread runs the
-        # reference's single-threaded Naive<> on its own row): ~5 s of wall clock at 16384^2 per row
+        # one step = one row of C per physical core (C rows are independent; every thread runs the reference's
+        # single-threaded Naive<> on its own row), restricted to the first SAMPLE_COLS columns so that W + K steps
+        # end within minutes.  The sample is FIXED: same rows, columns and thread count on every run of a box.
         threads = host_threads()
-        rows_per_step = threads
         rng = np.random.default_rng(5)
-        b = rng.uniform(1, 10, size=(K, M)).astype(np_dt)
-        a_rows = rng.uniform(1, 10, size=(rows_per_step, K)).astype(np_dt)
+        a_rows, b, cols = cpu_sample_inputs(np_dt, K, M, threads, rng=rng)
         kind = "reference"
-        # one untimed step; if the host is slower than expected, shrink the per-step sample (fewer rows,
-        # fewer threads) so that K timed steps stay within a few minutes
-        t_warm, _, _ = reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, K, M, threads)
-        if t_warm > 8.0:
-            threads = max(1, int(threads * 8.0 / t_warm))
-            rows_per_step = threads
-            a_rows = a_rows[:rows_per_step]
+        for _ in range(args.warmup):
+            reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, K, cols, threads)
         t = 0.0
         for _ in range(args.steps):
-            dt_s, kind, threads = reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, K, M, threads)
+            dt_s, kind, threads = reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, K, cols, threads)
             t += dt_s
-        sample_ops = 2.0 * rows_per_step * K * M
-        value = 1e-9 * sample_ops * args.steps / t
-        sample = ("%d rows of C per step (%d x %d x %d): the reference's Naive<> (single-threaded as written) on one "
-                  "row per host thread, %d threads" % (rows_per_step, rows_per_step, K, M, threads))
+        value = 1e-9 * 2.0 * threads * K * cols * args.steps / t
         print(json.dumps({
             "impl": "reference", "metric": metric_name, "value": value, "unit": metric, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_name,
             "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": value, "unit": metric, "cores": threads, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": metric, "cores": threads, "kind": kind,
+                             "sample": cpu_sample_text(threads, K, cols, threads)},
             "e2e": {"value": value, "unit": metric, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return 0
@@ -258,14 +294,17 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")  # CPU-side barrier: ranks that wait must not spin on their GPU
 
     t_dt = {"float": torch.float32, "half": torch.float16, "double": torch.float64}[dtype_name]
     dtype = G.DTYPE_FROM_NAME[dtype_name]
     mp, rd = G.OP_FROM_NAME[mp_name], G.OP_FROM_NAME[rd_name]
     es = torch.empty((), dtype=t_dt).element_size()
+    tune = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.tune.split(",") if kv}
 
     # row-block of this rank: ceil(N / world) rows, last block may be short
     rows_per = (N + world - 1) // world
@@ -282,6 +321,7 @@ def main():
         b_full = (torch.rand((K, M), generator=gen, device=dev, dtype=torch.float32) * (hi - lo) + lo).to(t_dt)
     else:
         b_full = torch.empty((K, M), device=dev, dtype=t_dt)
+    extra = {}
     if world > 1:
         dist.broadcast(b_full, src=0)  # the ONE collective of the path: B over NVLink/NVSwitch
         # reported beside the step time: the same broadcast once more, now that the
@@ -295,12 +335,13 @@ def main():
         torch.cuda.synchronize()
         tb = torch.tensor([eb0.elapsed_time(eb1)], device=dev, dtype=torch.float64)
         dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        config["broadcast_b_ms"] = round(float(tb.item()), 4)
-        config["broadcast_b_bytes"] = b_full.numel() * b_full.element_size()
+        extra["broadcast_b"] = {"ms": round(float(tb.item()), 4), "bytes": b_full.numel() * b_full.element_size(),
+                                "note": "one NCCL broadcast of B before the timed region (SURVEY.md 8e)"}
     c_blk = torch.empty((n_local, M), device=dev, dtype=t_dt)
     torch.cuda.synchronize()
 
     ctx = G.Context(local_rank)
+    ctx.set_tuning(**tune)
     # a dedicated (non-default) torch stream: its handle is what the C-ABI launches on and what the
     # torch.cuda.Event pairs below are recorded on (the default stream's handle is 0 == "use the
     # context's own stream" in the C-ABI)
@@ -326,19 +367,21 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     ctx.set_profiling(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    t_end = time.perf_counter()
     elapsed_ms = ev0.elapsed_time(ev1)
     prep_s, main_s, calls = ctx.profile_read()
     ctx.set_profiling(False)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     t_max = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -348,15 +391,18 @@ def main():
     value = 1e-9 * ops_total / (1e-3 * ms_per_step)  # whole job: all ranks' row-blocks
 
     # ---- light on-device sanity so that a wrong kernel cannot post a number (not the parity test)
-    if (mp_name, rd_name) == ("Multiply", "Add"):
-        rows = torch.tensor([0, n_local // 2, n_local - 1], device=dev)
-        ref = a_blk[rows].double() @ b_full.double()
-        got = c_blk[rows].double()
-        rel = ((got - ref).abs() / ref.abs().clamp_min(1e-30)).max().item()
+    def check_rows(got_rows, a_rows_t, what):
+        ref = a_rows_t.double() @ b_full.double()
+        rel = ((got_rows.double() - ref).abs() / ref.abs().clamp_min(1e-30)).max().item()
         tol = 1e-2 if dtype_name == "half" else 1e-3
         if not (rel <= tol):
-            raise SystemExit("bench.py: result check failed (max rel err %.3e > %.0e)" % (rel, tol))
-        config["check"] = "3 rows of C vs fp64 torch.matmul on device: max rel err %.2e" % rel
+            raise SystemExit("bench.py: %s result check failed (max rel err %.3e > %.0e)" % (what, rel, tol))
+        return rel
+
+    if (mp_name, rd_name) == ("Multiply", "Add"):
+        rows = torch.tensor([0, n_local // 2, n_local - 1], device=dev)
+        extra["check"] = "3 rows of C vs fp64 torch.matmul on device: max rel err %.2e" % check_rows(c_blk[rows], a_blk[rows],
+                                                                                                 "device-timed")
 
     out = None
     if rank == 0:
@@ -382,32 +428,24 @@ def main():
                          "(profiles/r01_exp_fp64_pipes.jsonl); datasheet 37; not in MEASURED_PEAKS.json")
             roof = {"bound": "tensor", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TFLOP/s"}
         else:
-            # derived CUDA-core issue ceiling: one warp instruction per clock and scheduler
-            # = 148 SMs x 4 x 32 lanes x 1.965 GHz = 37.2e12 lane-instructions/s, 2 ops per element-step.
-            #   float (Add, Min|Max): 1 FADD2 + 1 FMNMX3 per two element-steps = 1.0 slot per step -> 74.4 TOp/s
-            #     (the half-rate ALU pipe of the FMNMX3 gives the same bound); the inner loop alone, on a
-            #     resident tile, measures 44.8 TOp/s (scripts/exp_semiring_issue.cu)
-            #   anything else (e.g. float (Multiply, Add) under MM_FLAG_EXACT: 1 FMUL2 per two steps + 1 FADD
-            #     per step): 1.5 slots per step -> 49.6
-            fast_minmax = dtype_name == "float" and mp_name == "Add" and rd_name in ("Min", "Max") and not (flags & 2)
-            peak = 74.4 if fast_minmax else 49.6
-            peak_note = ("derived CUDA-core issue ceiling at 1965 MHz, %s (DESIGN.md 3.3)%s; neither HBM- nor "
-                         "tensor-bound" % ("1 FADD2 + 1 FMNMX3 per two element-steps" if fast_minmax else
-                                           "1.5 issue slots per element-step",
-                                           "; inner loop alone measured at 44.8 TOp/s (profiles/r01_exp_semiring_issue.jsonl)"
-                                           if fast_minmax else ""))
+            peak, peak_note = semiring_peak(dtype_name, mp_name, rd_name, flags)
             roof = {"bound": "cuda_core_issue", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TOp/s"}
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["kernel"] = path
         roof["kernel_ms"] = 1e3 * main_avg_s
         roof["prep_ms"] = 1e3 * prep_s / max(calls, 1)
+        roof["prep_note"] = ("exposed operand preparation before the main kernel starts (A's TF32 rounding); B's rounding "
+                             "runs concurrently with the GEMM and is inside kernel_ms" if path == "tcgen05_tf32" else "")
         roof["peak_source"] = peak_note
-        tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        traffic = None
-        if os.path.exists(tr_path):
-            traffic = json.load(open(tr_path)).get("%s@%s" % (path, args.workload))
-        roof["traffic"] = traffic
+        # DRAM bytes of the dominant kernel: only a figure MEASURED for exactly this workload, GPU count and
+        # default tuning (one `ncu --set full` capture per round, profiles/ncu_traffic.json); null otherwise
         roof["algorithmic_bytes"] = es * (n_local * K + K * M + n_local * M)
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tr_path) and not tune and flags == 0:
+            traffic = json.load(open(tr_path)).get("%s@%s@n%d" % (path, args.workload, world))
+        roof["traffic"] = traffic
+        roof["traffic_ratio"] = (traffic / roof["algorithmic_bytes"]) if traffic else None
 
         out = {"metric": metric_name, "value": value, "unit": metric, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -415,45 +453,69 @@ def main():
                                               "half": "f16 multiply, f32 accumulate", "double": "f64"}[dtype_name]
                if (mp_name, rd_name) == ("Multiply", "Add") else "f32",
                "data": "synthetic", "config": config, "clocks": clocks, "roofline": roof,
-               # NVML board power during the timed region (the reference's PSU power meter);
-               # meaningful for runs of a second or more (nvidia-smi refreshes every ~100 ms)
+               # NVML board power during the timed region (the reference's PSU power meter)
                "energy": ({"avg_power_w": clocks["power_w_avg_under_load"],
-                           "gop_per_joule": value / clocks["power_w_avg_under_load"]}
+                           "gop_per_joule": value / clocks["power_w_avg_under_load"] / world, "scope": "GPU 0 only"}
                           if clocks and clocks.get("power_w_avg_under_load") else None),
                "gpu_launches": args.steps * G.launch_count(dtype, mp, rd, flags)}
+        out.update(extra)
+        if tune:
+            out["tuning"] = tune
 
     # ------------------------------------------------------------------ e2e: host buffers through the C-ABI
+    # The call a user of the reference makes: ONE blocking MatrixMultiplicationKernel(a, b, c, n, k, m) on host
+    # pointers (include/MatrixMultiplication.h:155-171).  Rank 0 issues it for the WHOLE problem; with N > 1 the
+    # library splits it over all N GPUs itself (mm_multi_gemm_host: A row-blocks and 1/N of B per GPU over PCIe,
+    # B assembled GPU-to-GPU over NVLink, C row-blocks back).  The other ranks wait on the CPU and leave their
+    # GPUs idle.
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, 3))
-        a_host = torch.empty((n_local, K), dtype=t_dt, pin_memory=True)
-        b_host = torch.empty((K, M), dtype=t_dt, pin_memory=True)
-        c_host = torch.empty((n_local, M), dtype=t_dt, pin_memory=True)
-        a_host.copy_(a_blk)
-        b_host.copy_(b_full)
-        torch.cuda.synchronize()
-        a_np, b_np, c_np = a_host.numpy(), b_host.numpy(), c_host.numpy()
-        ctx.gemm_host(dtype, mp, rd, a_np, b_np, n_local, K, M, flags=flags, out=c_np)  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            ctx.gemm_host(dtype, mp, rd, a_np, b_np, n_local, K, M, flags=flags, out=c_np)
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        t_e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        e2e_s = 0.0
+        if rank == 0:
+            a_host = torch.empty((N, K), dtype=t_dt, pin_memory=True)
+            b_host = torch.empty((K, M), dtype=t_dt, pin_memory=True)
+            c_host = torch.empty((N, M), dtype=t_dt, pin_memory=True)
+            g2 = torch.Generator(device=dev)
+            g2.manual_seed(99)
+            for i in range(0, N, 2048):   # the other ranks' row-blocks are synthetic too: draw all of A here
+                rows_i = min(2048, N - i)
+                blk = (torch.rand((rows_i, K), generator=g2, device=dev, dtype=torch.float32) * (hi - lo) + lo).to(t_dt)
+                a_host[i:i + rows_i].copy_(blk)
+            b_host.copy_(b_full)
+            torch.cuda.synchronize()
+            a_np, b_np, c_np = a_host.numpy(), b_host.numpy(), c_host.numpy()
+            runner = ctx if world == 1 else G.Multi(world)
+            if world > 1:
+                runner.set_tuning(**tune)
+            runner.gemm_host(dtype, mp, rd, a_np, b_np, N, K, M, flags=flags, out=c_np)  # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                runner.gemm_host(dtype, mp, rd, a_np, b_np, N, K, M, flags=flags, out=c_np)
+            e2e_s = (time.perf_counter() - t0) / e2e_steps
+            note = ("mm_gemm_host(): pinned host A, B -> device, kernels, C -> pinned host; wall clock" if world == 1 else
+                    "mm_multi_gemm_host() from rank 0 over all %d GPUs (peer access: %s): per GPU 1/%d of A and of B over "
+                    "PCIe, B gathered over NVLink by the library's kernels, C row-blocks back; wall clock"
+                    % (world, runner.peer_access, world))
+            e2e_check = None
+            if (mp_name, rd_name) == ("Multiply", "Add"):
+                idx = [0, N // 2 + 1, N - 1]
+                e2e_check = check_rows(c_host[idx].to(dev), a_host[idx].to(dev), "e2e")
+            out["e2e"] = {"value": 1e-9 * ops_total / e2e_s, "unit": metric,
+                          "h2d_bytes_per_step": int(es * (N * K + K * M)), "d2h_bytes_per_step": int(es * N * M),
+                          "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s, "note": note,
+                          "check": ("3 rows of the host C vs fp64: max rel err %.2e" % e2e_check) if e2e_check is not None else None}
+            if world > 1:
+                runner.close()
+            del a_host, c_host
         if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        if out is not None:
-            out["e2e"] = {"value": 1e-9 * ops_total / float(t_e.item()), "unit": metric,
-                          "h2d_bytes_per_step": int(es * (n_local * K + K * M)),
-                          "d2h_bytes_per_step": int(es * n_local * M), "steps": e2e_steps,
-                          "note": "mm_gemm_host(): pinned host A,B -> device, kernels, C -> pinned host; wall clock, max over ranks"}
-        del a_host, c_host
+            dist.barrier(group=host_group)
 
     # ------------------------------------------------------------------ cpu_baseline (rank 0, N == 1)
     if out is not None and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline_line(dtype_name, mp_name, rd_name, metric, K, M,
                                                 lambda rows: a_blk[:min(rows, n_local)].cpu().numpy(),
-                                                b_full.cpu().numpy())
+                                                b_full[:, :min(SAMPLE_COLS, M)].cpu().numpy())
 
     if out is not None:
         print(json.dumps(out))
@@ -461,6 +523,20 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def semiring_peak(dtype_name, mp_name, rd_name, flags):
+    """Derived CUDA-core issue ceiling: one warp instruction per clock and scheduler
+    = 148 SMs x 4 x 32 lanes x 1.965 GHz = 37.2e12 lane-instructions/s, 2 ops per element-step.
+      float (Add, Min|Max): 1 FADD2 + 1 FMNMX3 per two element-steps = 1.0 slot per step -> 74.4 TOp/s
+        (the half-rate ALU pipe of the FMNMX3 gives the same bound)
+      anything else (e.g. float (Multiply, Add) under MM_FLAG_EXACT: 1 FMUL2 per two steps + 1 FADD per step):
+        1.5 slots per step -> 49.6"""
+    fast_minmax = dtype_name == "float" and mp_name == "Add" and rd_name in ("Min", "Max") and not (flags & 2)
+    peak = 74.4 if fast_minmax else 49.6
+    note = ("derived CUDA-core issue ceiling at 1965 MHz, %s (DESIGN.md 3.3); neither HBM- nor tensor-bound"
+            % ("1 FADD2 + 1 FMNMX3 per two element-steps" if fast_minmax else "1.5 issue slots per element-step"))
+    return peak, note
 
 
 if __name__ == "__main__":

@@ -32,10 +32,22 @@ DTYPE_FROM_NAME = {"half": HALF, "float": FLOAT, "double": DOUBLE, "int": INT32,
 OP_FROM_NAME = {"Multiply": MULTIPLY, "Product": MULTIPLY, "Add": ADD, "Sum": ADD,
                 "Min": MIN, "Max": MAX, "And": AND}
 
+# MM_TUNE_* knobs (include/mm_b200.h)
+(TUNE_CTA_GROUP, TUNE_BLOCK_N, TUNE_STAGES, TUNE_RASTER_ROWS, TUNE_TILE_SYNC, TUNE_B_MN, TUNE_L2_POLICY,
+ TUNE_B_OVERLAP, TUNE_TMA_STORE, TUNE_DMMA_TILE_ROWS, TUNE_EXPERIMENT_TF32_NO_ROUND) = range(11)
+TUNE_NAMES = {"cta_group": TUNE_CTA_GROUP, "block_n": TUNE_BLOCK_N, "stages": TUNE_STAGES,
+              "raster_rows": TUNE_RASTER_ROWS, "tile_sync": TUNE_TILE_SYNC, "b_mn": TUNE_B_MN,
+              "l2_policy": TUNE_L2_POLICY, "b_overlap": TUNE_B_OVERLAP, "tma_store": TUNE_TMA_STORE,
+              "dmma_tile_rows": TUNE_DMMA_TILE_ROWS, "tf32_no_round": TUNE_EXPERIMENT_TF32_NO_ROUND}
+
 EXPORTS = ["mm_last_error", "mm_version", "mm_dtype_size", "mm_memory_width", "mm_context_create",
            "mm_context_destroy", "mm_buffer_alloc", "mm_buffer_free", "mm_copy_to_device",
            "mm_copy_to_host", "mm_kernel_execute", "mm_kernel_enqueue", "mm_kernel_launch_count",
-           "mm_kernel_path", "mm_gemm_host", "mm_context_set_profiling", "mm_context_profile_read"]
+           "mm_kernel_path", "mm_gemm_host", "mm_context_set_profiling", "mm_context_profile_read",
+           "mm_context_set_tuning", "mm_context_get_tuning", "mm_context_reserve",
+           "mm_multi_create", "mm_multi_destroy", "mm_multi_device_count", "mm_multi_context",
+           "mm_multi_peer_access", "mm_multi_gemm_host", "mm_multi_upload", "mm_multi_execute",
+           "mm_multi_download"]
 
 
 class MMError(RuntimeError):
@@ -75,6 +87,18 @@ def lib():
         L.mm_gemm_host.argtypes = [vp, i, i, i, i, vp, vp, vp, u, u, u, dp, dp]
         L.mm_context_set_profiling.argtypes = [vp, i]
         L.mm_context_profile_read.argtypes = [vp, dp, dp, ctypes.POINTER(i)]
+        L.mm_context_set_tuning.argtypes = [vp, i, i]
+        L.mm_context_get_tuning.argtypes = [vp, i, ctypes.POINTER(i)]
+        L.mm_context_reserve.argtypes = [vp, i, i, u, u, u]
+        L.mm_multi_create.argtypes = [i, ctypes.POINTER(i), ctypes.POINTER(vp)]
+        L.mm_multi_destroy.argtypes = [vp]
+        L.mm_multi_device_count.argtypes = [vp]
+        L.mm_multi_context.argtypes, L.mm_multi_context.restype = [vp, i], vp
+        L.mm_multi_peer_access.argtypes = [vp]
+        L.mm_multi_gemm_host.argtypes = [vp, i, i, i, i, vp, vp, vp, u, u, u, dp, dp]
+        L.mm_multi_upload.argtypes = [vp, i, i, vp, vp, u, u, u]
+        L.mm_multi_execute.argtypes = [vp, i, i, i, i, u, u, u, dp, dp]
+        L.mm_multi_download.argtypes = [vp, i, vp, u, u]
         _lib = L
     return _lib
 
@@ -151,6 +175,19 @@ class Context:
         _check(lib().mm_kernel_enqueue(self._h, dtype, map_op, reduce_op, flags, a_dev, b_dev, c_dev,
                                        n, k, m, ctypes.c_void_p(stream) if stream else None))
 
+    def set_tuning(self, **knobs):
+        """mm_context_set_tuning by name, e.g. ctx.set_tuning(cta_group=1, stages=4)."""
+        for name, value in knobs.items():
+            _check(lib().mm_context_set_tuning(self._h, TUNE_NAMES[name], int(value)))
+
+    def get_tuning(self, name):
+        v = ctypes.c_int()
+        _check(lib().mm_context_get_tuning(self._h, TUNE_NAMES[name], ctypes.byref(v)))
+        return v.value
+
+    def reserve(self, dtype, n, k, m, flags=0):
+        _check(lib().mm_context_reserve(self._h, dtype, flags, n, k, m))
+
     def set_profiling(self, enable=True):
         _check(lib().mm_context_set_profiling(self._h, int(enable)))
 
@@ -165,7 +202,76 @@ class Context:
         return _gemm_host(self._h, dtype, map_op, reduce_op, a, b, n, k, m, flags, out)
 
 
-def _gemm_host(handle, dtype, map_op, reduce_op, a, b, n, k, m, flags, out):
+class _BorrowedContext(Context):
+    """A per-device context owned by a Multi (never destroyed from Python)."""
+
+    def __init__(self, handle, device):
+        self._h = ctypes.c_void_p(handle)
+        self.device = device
+
+    def close(self):
+        self._h = ctypes.c_void_p()
+
+
+class Multi:
+    """C row-blocks over G GPUs of this process (mm_multi_*): one blocking call on
+    host arrays, or the device-resident upload / execute / download lifecycle of RunHardware."""
+
+    def __init__(self, n_gpus, devices=None):
+        self._h = ctypes.c_void_p()
+        dev = (ctypes.c_int * n_gpus)(*devices) if devices is not None else None
+        _check(lib().mm_multi_create(n_gpus, dev, ctypes.byref(self._h)))
+        self.n_gpus = n_gpus
+
+    def close(self):
+        if self._h:
+            lib().mm_multi_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def peer_access(self):
+        return bool(lib().mm_multi_peer_access(self._h))
+
+    def context(self, index):
+        return _BorrowedContext(lib().mm_multi_context(self._h, index), index)
+
+    def set_tuning(self, **knobs):
+        for g in range(self.n_gpus):
+            self.context(g).set_tuning(**knobs)
+
+    def gemm_host(self, dtype, map_op, reduce_op, a, b, n, k, m, flags=0, out=None):
+        return _gemm_host(self._h, dtype, map_op, reduce_op, a, b, n, k, m, flags, out, fn=lib().mm_multi_gemm_host)
+
+    def upload(self, dtype, a, b, n, k, m, flags=0):
+        npdt = NP_DTYPE[dtype]
+        a = np.ascontiguousarray(a, dtype=npdt).reshape(-1)
+        b = np.ascontiguousarray(b, dtype=npdt).reshape(-1)
+        _check(lib().mm_multi_upload(self._h, dtype, flags, a.ctypes.data, b.ctypes.data, n, k, m))
+
+    def execute(self, dtype, map_op, reduce_op, n, k, m, flags=0):
+        sd, sw = ctypes.c_double(), ctypes.c_double()
+        _check(lib().mm_multi_execute(self._h, dtype, map_op, reduce_op, flags, n, k, m, ctypes.byref(sd), ctypes.byref(sw)))
+        return sd.value, sw.value
+
+    def download(self, dtype, n, m):
+        c = np.empty((n, m), dtype=NP_DTYPE[dtype])
+        _check(lib().mm_multi_download(self._h, dtype, c.ctypes.data, n, m))
+        return c
+
+
+def _gemm_host(handle, dtype, map_op, reduce_op, a, b, n, k, m, flags, out, fn=None):
     npdt = NP_DTYPE.get(dtype)  # unknown codes are rejected by the library itself (MM_ERR_INVALID)
     a = np.ascontiguousarray(a, dtype=npdt).reshape(-1)
     b = np.ascontiguousarray(b, dtype=npdt).reshape(-1)
@@ -173,8 +279,8 @@ def _gemm_host(handle, dtype, map_op, reduce_op, a, b, n, k, m, flags, out):
         raise MMError(1, "A must hold n*k and B k*m elements")
     c = out if out is not None else np.empty((n, m), dtype=npdt if npdt is not None else a.dtype)
     sd, sw = ctypes.c_double(), ctypes.c_double()
-    _check(lib().mm_gemm_host(handle, dtype, map_op, reduce_op, flags, a.ctypes.data, b.ctypes.data,
-                              c.ctypes.data, n, k, m, ctypes.byref(sd), ctypes.byref(sw)))
+    _check((fn or lib().mm_gemm_host)(handle, dtype, map_op, reduce_op, flags, a.ctypes.data, b.ctypes.data,
+                                      c.ctypes.data, n, k, m, ctypes.byref(sd), ctypes.byref(sw)))
     return c, sd.value, sw.value
 
 

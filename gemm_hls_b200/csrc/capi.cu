@@ -1,11 +1,15 @@
 // C-ABI of libmm_b200.so (include/mm_b200.h): context / buffer lifecycle mirroring the
-// hlslib::ocl calls of host/RunHardware.cpp:116-190, and the dispatch of one
-// MatrixMultiplicationKernel invocation onto the B200 kernel families.
+// hlslib::ocl calls of host/RunHardware.cpp:116-190, the dispatch of one
+// MatrixMultiplicationKernel invocation onto the B200 kernel families, the pipelined host-pointer
+// entry (test/TestSimulation.cpp:66) and its row-block split over the GPUs of one box.
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -22,16 +26,77 @@ int fail(int code, const std::string &msg) {
   return code;
 }
 
+namespace {
+
+struct KnobInfo {
+  const char *env;
+  int dflt;
+};
+// index = MM_TUNE_* (include/mm_b200.h)
+const KnobInfo kKnobs[MM_TUNE_COUNT] = {
+    {"MM_TCGEN05_CTA_GROUP", 2}, {"MM_TCGEN05_BLOCK_N", 256},  {"MM_TCGEN05_STAGES", 0},
+    {"MM_TCGEN05_RASTER_ROWS", 2048}, {"MM_TCGEN05_TILE_SYNC", 1}, {"MM_TCGEN05_B_MN", 1},
+    {"MM_TCGEN05_L2", 0}, {"MM_TCGEN05_B_OVERLAP", 1}, {"MM_TCGEN05_TMA_STORE", 1},
+    {"MM_DMMA_TILE_ROWS", 0}, {"MM_EXPERIMENT_TF32_NO_ROUND", 0},
+};
+
+}  // namespace
+
+int tuning_validate(int knob, int value) {
+  bool ok = false;
+  switch (knob) {
+    case MM_TUNE_TCGEN05_CTA_GROUP: ok = value == 1 || value == 2; break;
+    case MM_TUNE_TCGEN05_BLOCK_N: ok = value == 128 || value == 256; break;
+    case MM_TUNE_TCGEN05_STAGES: ok = value == 0 || (value >= 2 && value <= 8); break;
+    case MM_TUNE_TCGEN05_RASTER_ROWS: ok = value >= 1; break;
+    case MM_TUNE_TCGEN05_L2_POLICY: ok = value >= 0 && value <= 2; break;
+    case MM_TUNE_DMMA_TILE_ROWS: ok = value == 0 || value == 64 || value == 128; break;
+    case MM_TUNE_TCGEN05_TILE_SYNC:
+    case MM_TUNE_TCGEN05_B_MN:
+    case MM_TUNE_TCGEN05_B_OVERLAP:
+    case MM_TUNE_TCGEN05_TMA_STORE:
+    case MM_TUNE_EXPERIMENT_TF32_NO_ROUND: ok = value == 0 || value == 1; break;
+    default: return fail(MM_ERR_INVALID, "unknown tuning knob " + std::to_string(knob));
+  }
+  if (!ok) {
+    return fail(MM_ERR_INVALID, std::string("value ") + std::to_string(value) + " is out of range for tuning knob " +
+                                    kKnobs[knob].env);
+  }
+  return MM_OK;
+}
+
+Tuning default_tuning() {
+  Tuning t;
+  for (int i = 0; i < MM_TUNE_COUNT; ++i) {
+    t.v[i] = kKnobs[i].dflt;
+    const char *e = std::getenv(kKnobs[i].env);
+    if (!e || !*e) continue;
+    int value;
+    if (i == MM_TUNE_TCGEN05_L2_POLICY && (e[0] == 'n' || e[0] == 'f' || e[0] == 'l')) {
+      value = e[0] == 'f' ? 1 : (e[0] == 'l' ? 2 : 0);  // normal / first / last, as the round-1 scripts spell it
+    } else {
+      value = std::atoi(e);
+    }
+    if (tuning_validate(i, value) == MM_OK) t.v[i] = value;  // an out-of-range environment value is ignored
+  }
+  return t;
+}
+
 }  // namespace mm
 
 struct mm_context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;                         // B's operand preparation, overlapped with the GEMM
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // H2D / D2H streams of the pipelined host path
-  std::vector<cudaEvent_t> sync_events;                // untimed events ordering the three streams
-  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  std::vector<cudaEvent_t> sync_events;                // untimed events ordering the streams
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_slice = nullptr;                      // multi-GPU: this device's slice of B has arrived
   mm::Scratch scratch;       // operand copies of the tensor-core path
-  mm::Scratch staging[3];    // device A, B, C of mm_gemm_host
+  mm::Scratch staging[3];    // device A, B, C of the host-pointer entries
+  std::vector<void *> retired;  // superseded scratch allocations a captured graph may still reference
+  bool captured = false;        // a stream capture has gone through this context
+  mm::Tuning tuning;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;  // 3 per profiled call: start, after prep, after main
   int prof_calls = 0;
@@ -48,16 +113,24 @@ bool valid_op(int o) { return o >= 0 && o < MM_OP_COUNT; }
 
 enum Path { kPathTcgen05, kPathDmma, kPathSemiring };
 
-Path select_path(int dtype, int map_op, int reduce_op, int flags) {
+Path select_path(int dtype, int map_op, int reduce_op, int flags, unsigned n) {
   const bool dense = (map_op == MM_OP_MULTIPLY && reduce_op == MM_OP_ADD) && !(flags & MM_FLAG_EXACT);
   if (dense && (dtype == MM_DTYPE_FLOAT || dtype == MM_DTYPE_HALF)) return kPathTcgen05;
-  if (dense && dtype == MM_DTYPE_DOUBLE) return kPathDmma;
+  if (dense && dtype == MM_DTYPE_DOUBLE) {
+    // the DMMA kernel reads a transposed A through 16-byte boxes: needs an even N
+    return ((flags & MM_FLAG_TRANSPOSED_A) && (n % 2 != 0)) ? kPathSemiring : kPathDmma;
+  }
   return kPathSemiring;
 }
 
-int ensure(mm::Scratch &s, size_t bytes) {
+// Grow `s` to at least `bytes`.  `keep_old`: the superseded allocation stays alive (a captured CUDA
+// graph may hold its address) and is freed with the context.
+int ensure(mm_context *ctx, mm::Scratch &s, size_t bytes, bool keep_old) {
   if (s.bytes >= bytes) return MM_OK;
-  if (s.ptr) cudaFree(s.ptr);
+  if (s.ptr) {
+    if (keep_old) ctx->retired.push_back(s.ptr);
+    else cudaFree(s.ptr);
+  }
   s.ptr = nullptr;
   s.bytes = 0;
   cudaError_t e = cudaMalloc(&s.ptr, bytes);
@@ -88,11 +161,33 @@ int check_args(int dtype, int map_op, int reduce_op, const void *a, const void *
   return MM_OK;
 }
 
+// The kernels use 128-bit global accesses and TMA descriptors on A, B and C.
+int check_device_alignment(const void *a, const void *b, const void *c) {
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) % 16 != 0) {
+    return fail(MM_ERR_INVALID, "device matrix pointers must be 16-byte aligned");
+  }
+  return MM_OK;
+}
+
+mm::GemmArgs make_args(mm_context *ctx, const void *a, const void *b, void *c, unsigned n, unsigned k, unsigned m,
+                       int flags, cudaStream_t stream) {
+  mm::GemmArgs g{a, b, c, n, k, m, flags, stream};
+  g.tuning = &ctx->tuning;
+  g.side_stream = ctx->side;
+  g.ev_fork = ctx->ev_fork;
+  g.ev_join = ctx->ev_join;
+  return g;
+}
+
 int enqueue_locked(mm_context *ctx, int dtype, int map_op, int reduce_op, int flags, const void *a,
                    const void *b, void *c, unsigned n, unsigned k, unsigned m, cudaStream_t stream,
                    bool dry_run = false) {
-  mm::GemmArgs g{a, b, c, n, k, m, flags, stream};
+  mm::GemmArgs g = make_args(ctx, a, b, c, n, k, m, flags, stream);
   g.dry_run = dry_run;
+  cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &capture) == cudaSuccess && capture != cudaStreamCaptureStatusNone) {
+    ctx->captured = true;
+  }
   cudaEvent_t *pe = nullptr;
   if (!dry_run && ctx->profiling && ctx->prof_calls < 256) {
     while (ctx->prof_events.size() < size_t(3 * (ctx->prof_calls + 1))) {
@@ -107,12 +202,13 @@ int enqueue_locked(mm_context *ctx, int dtype, int map_op, int reduce_op, int fl
     MM_CUDA_TRY(cudaEventRecord(pe[0], stream));
   }
   int rc_launch = MM_OK;
-  Path path = select_path(dtype, map_op, reduce_op, flags);
-  if (path == kPathDmma && (flags & MM_FLAG_TRANSPOSED_A) && (n % 2 != 0)) path = kPathSemiring;
-  switch (path) {
+  switch (select_path(dtype, map_op, reduce_op, flags, n)) {
     case kPathTcgen05: {
-      const size_t need = mm::tcgen05_scratch_bytes(dtype, n, k, m, flags);
-      int rc = ensure(ctx->scratch, need);
+      const size_t need = mm::tcgen05_scratch_bytes(dtype, n, k, m, flags, ctx->tuning);
+      if (need > ctx->scratch.bytes && capture != cudaStreamCaptureStatusNone) {
+        return fail(MM_ERR_INVALID, "the scratch cannot grow during stream capture: call mm_context_reserve() first");
+      }
+      int rc = ensure(ctx, ctx->scratch, need, ctx->captured);
       if (rc != MM_OK) return rc;
       rc_launch = mm::launch_tcgen05(dtype, g, ctx->scratch.ptr, ctx->scratch.bytes);
       break;
@@ -131,8 +227,378 @@ int enqueue_locked(mm_context *ctx, int dtype, int map_op, int reduce_op, int fl
   return MM_OK;
 }
 
+void destroy_context(mm_context *ctx) {
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->side) cudaStreamSynchronize(ctx->side);
+  if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
+  for (auto &s : ctx->staging) {
+    if (s.ptr) cudaFree(s.ptr);
+  }
+  for (void *p : ctx->retired) cudaFree(p);
+  for (auto e : ctx->prof_events) cudaEventDestroy(e);
+  for (auto e : ctx->sync_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : {ctx->ev_start, ctx->ev_stop, ctx->ev_fork, ctx->ev_join, ctx->ev_slice}) {
+    if (e) cudaEventDestroy(e);
+  }
+  for (cudaStream_t s : {ctx->copy_in, ctx->copy_out, ctx->side, ctx->stream}) {
+    if (s) cudaStreamDestroy(s);
+  }
+  delete ctx;
+}
+
+int init_context(mm_context *ctx) {
+  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+  MM_CUDA_TRY(cudaEventCreate(&ctx->ev_start));
+  MM_CUDA_TRY(cudaEventCreate(&ctx->ev_stop));
+  MM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  MM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  MM_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_slice, cudaEventDisableTiming));
+  return MM_OK;
+}
+
+// ---- the pipelined host-pointer path --------------------------------------------------------------
+// How B reaches the device of one pipeline.  Single GPU: the whole of B over PCIe.  Multi-GPU: this
+// device uploads rows [k0, k1) only; the other slices are read from the peers' B buffers over NVLink
+// (`parts_dev`: device array of `parts` base pointers, slice j = rows [j * part_rows, ...)).
+struct BPlan {
+  unsigned k0 = 0, k1 = 0;
+  const void *const *parts_dev = nullptr;
+  unsigned parts = 1, part_rows = 0;
+  std::vector<cudaEvent_t> peer_slices;  // the peers' "slice uploaded" events (recorded before this is used)
+};
+
+struct Pipeline {
+  mm_context *ctx;
+  int dtype, map_op, reduce_op, flags;
+  const unsigned char *a_host;  // this pipeline's rows of A (row-major) or all of A (transposed)
+  const unsigned char *b_host;  // all of B
+  unsigned char *c_host;        // this pipeline's rows of C
+  unsigned rows, k, m;
+  size_t es;
+  Path path;
+  unsigned char *da = nullptr, *db = nullptr, *dc = nullptr;
+
+  // Phase 1: allocations + this device's (slice of) B on its way.  Records ctx->ev_slice.
+  int upload_b(const BPlan &bp) {
+    MM_CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->staging[0], size_t(rows) * k * es, false)) != MM_OK) return rc;
+    if ((rc = ensure(ctx, ctx->staging[1], size_t(k) * m * es, false)) != MM_OK) return rc;
+    if ((rc = ensure(ctx, ctx->staging[2], size_t(rows) * m * es, false)) != MM_OK) return rc;
+    if (path == kPathTcgen05) {
+      rc = ensure(ctx, ctx->scratch, mm::tcgen05_scratch_bytes(dtype, rows, k, m, flags, ctx->tuning), ctx->captured);
+      if (rc != MM_OK) return rc;
+    }
+    da = static_cast<unsigned char *>(ctx->staging[0].ptr);
+    db = static_cast<unsigned char *>(ctx->staging[1].ptr);
+    dc = static_cast<unsigned char *>(ctx->staging[2].ptr);
+    const size_t off = size_t(bp.k0) * m * es, bytes = size_t(bp.k1 - bp.k0) * m * es;
+    if (bytes) MM_CUDA_TRY(cudaMemcpyAsync(db + off, b_host + off, bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+    MM_CUDA_TRY(cudaEventRecord(ctx->ev_slice, ctx->copy_in));
+    return MM_OK;
+  }
+
+  // Phase 2: A row-chunks in, kernels, C row-chunks out; blocking.  C row-blocks are independent
+  // (kernel/Compute.cpp:53-56), so the H2D copy of A chunk i+1, the kernels of chunk i and the D2H
+  // copy of C chunk i-1 run concurrently on three streams; B is assembled (and, on the tcgen05 path,
+  // prepared — overlapped with the first chunk's GEMM) once.  A stored K x N cannot be cut into
+  // contiguous row chunks: single chunk.
+  int run(const BPlan &bp, double *seconds_device) {
+    const int rc = enqueue_all(bp);
+    // drain every stream before returning, on the error paths too: the caller's host buffers must
+    // not be touched by copies in flight after this call has returned
+    cudaError_t e = cudaSuccess;
+    for (cudaStream_t s : {ctx->copy_in, ctx->side, ctx->stream, ctx->copy_out}) {
+      const cudaError_t es_ = cudaStreamSynchronize(s);
+      if (e == cudaSuccess) e = es_;
+    }
+    if (rc != MM_OK) return rc;
+    if (e != cudaSuccess) return fail(MM_ERR_CUDA, std::string("host pipeline: ") + cudaGetErrorString(e));
+    if (seconds_device) {
+      // first kernel start .. last kernel end on the compute stream (with more than one chunk this
+      // includes the stalls waiting for A chunks to arrive)
+      float ms = 0.f;
+      MM_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
+      *seconds_device = 1e-3 * ms;
+    }
+    return MM_OK;
+  }
+
+ private:
+  int enqueue_all(const BPlan &bp) {
+    MM_CUDA_TRY(cudaSetDevice(ctx->device));
+    const bool ta = (flags & MM_FLAG_TRANSPOSED_A) != 0;
+    const mm::Tuning &t = ctx->tuning;
+    unsigned chunk_rows = rows;
+    if (!ta) {
+      const size_t row_bytes = size_t(k) * es;
+      size_t cr = std::max<size_t>((rows + 15) / 16, ((size_t(32) << 20) + row_bytes - 1) / row_bytes);
+      if (const char *e = std::getenv("MM_HOST_CHUNK_ROWS")) cr = std::max(1, std::atoi(e));  // tests force small chunks
+      cr = (cr + 127) / 128 * 128;
+      if (cr < rows) chunk_rows = unsigned(cr);
+    }
+    const unsigned chunks = (rows + chunk_rows - 1) / chunk_rows;
+    while (ctx->sync_events.size() < size_t(2 * chunks)) {
+      cudaEvent_t e;
+      MM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->sync_events.push_back(e);
+    }
+    auto ev_a = [&](unsigned i) { return ctx->sync_events[i]; };
+    auto ev_c = [&](unsigned i) { return ctx->sync_events[chunks + i]; };
+
+    // ---- H2D stream: A chunks (B's slice went first, in upload_b)
+    for (unsigned i = 0; i < chunks; ++i) {
+      const size_t r0 = size_t(i) * chunk_rows, nr = std::min<size_t>(chunk_rows, rows - r0);
+      if (!ta) {
+        MM_CUDA_TRY(cudaMemcpyAsync(da + r0 * k * es, a_host + r0 * k * es, nr * k * es, cudaMemcpyHostToDevice,
+                                    ctx->copy_in));
+      } else {
+        MM_CUDA_TRY(cudaMemcpyAsync(da, a_host, size_t(rows) * k * es, cudaMemcpyHostToDevice, ctx->copy_in));
+      }
+      MM_CUDA_TRY(cudaEventRecord(ev_a(i), ctx->copy_in));
+    }
+
+    // ---- compute stream: B complete on this device (own slice + the peers' slices in place)
+    MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_slice, 0));
+    for (cudaEvent_t e : bp.peer_slices) MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, e, 0));
+    MM_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
+    mm::BSource src;
+    src.b = db;
+    if (bp.parts > 1) {
+      src.src = bp.parts_dev;
+      src.parts = bp.parts;
+      src.part_rows = bp.part_rows;
+    }
+    int rc = MM_OK;
+    mm::PreparedB pb;
+    unsigned char *aprep = nullptr;
+    if (path == kPathTcgen05) {
+      rc = mm::tcgen05_prepare_b_async(dtype, src, db, ctx->scratch.ptr, ctx->scratch.bytes, k, m, flags, t, ctx->stream,
+                                       ctx->side, ctx->ev_fork, ctx->ev_join, &pb);
+      if (rc != MM_OK) return rc;
+      aprep = static_cast<unsigned char *>(ctx->scratch.ptr) + mm::tcgen05_bt_bytes(dtype, k, m, flags, t);
+    } else if (bp.parts > 1) {
+      rc = mm::gather_b_rows(src, db, es, k, m, ctx->stream);  // the peers' slices into this GPU's B, over NVLink
+      if (rc != MM_OK) return rc;
+    }
+    for (unsigned i = 0; i < chunks && rc == MM_OK; ++i) {
+      const size_t r0 = size_t(i) * chunk_rows, nr = std::min<size_t>(chunk_rows, rows - r0);
+      MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev_a(i), 0));
+      const void *a_chunk = da + (ta ? 0 : r0 * k * es);
+      void *c_chunk = dc + r0 * m * es;
+      if (path == kPathTcgen05) {
+        const void *a_op = nullptr;
+        const size_t a_scale = (dtype == MM_DTYPE_FLOAT && (flags & MM_FLAG_TF32X3)) ? 3 : 1;
+        rc = mm::tcgen05_prepare_a(dtype, a_chunk, aprep + (ta ? 0 : r0 * k * es * a_scale), unsigned(nr), k, flags, t,
+                                   &a_op, ctx->stream);
+        if (rc == MM_OK) {
+          const mm::Tcgen05Counters cnt = mm::tcgen05_counters(ctx->scratch.ptr, ctx->scratch.bytes);
+          rc = mm::tcgen05_gemm(dtype, a_op, pb.b_op, c_chunk, unsigned(nr), k, m, flags, t, cnt.tile_sync, pb.ready,
+                                pb.ready_target, ctx->stream);
+        }
+      } else {
+        mm::GemmArgs g = make_args(ctx, a_chunk, db, c_chunk, unsigned(nr), k, m, flags, ctx->stream);
+        rc = (path == kPathDmma) ? mm::launch_dmma(g) : mm::launch_semiring(dtype, map_op, reduce_op, g);
+      }
+      if (rc == MM_OK) MM_CUDA_TRY(cudaEventRecord(ev_c(i), ctx->stream));
+    }
+    if (path == kPathTcgen05 && pb.forked) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+    if (rc != MM_OK) return rc;
+    MM_CUDA_TRY(cudaEventRecord(ctx->ev_stop, ctx->stream));
+
+    // ---- D2H stream
+    for (unsigned i = 0; i < chunks; ++i) {
+      const size_t r0 = size_t(i) * chunk_rows, nr = std::min<size_t>(chunk_rows, rows - r0);
+      MM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ev_c(i), 0));
+      MM_CUDA_TRY(cudaMemcpyAsync(c_host + r0 * m * es, dc + r0 * m * es, nr * m * es, cudaMemcpyDeviceToHost,
+                                  ctx->copy_out));
+    }
+    return MM_OK;
+  }
+};
+
 std::mutex g_default_mutex;
 mm_context *g_default_ctx = nullptr;
+mm_multi *g_default_multi = nullptr;
+
+int env_int(const char *name, int fallback) {
+  const char *e = std::getenv(name);
+  return (e && *e) ? std::atoi(e) : fallback;
+}
+
+// Reusable host barrier for the worker threads of one multi-GPU call.
+class HostBarrier {
+ public:
+  explicit HostBarrier(int n) : n_(n) {}
+  void arrive_and_wait() {
+    std::unique_lock<std::mutex> lock(m_);
+    const int gen = gen_;
+    if (++count_ == n_) {
+      count_ = 0;
+      ++gen_;
+      cv_.notify_all();
+    } else {
+      cv_.wait(lock, [&] { return gen_ != gen; });
+    }
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  int n_, count_ = 0, gen_ = 0;
+};
+
+}  // namespace
+
+struct mm_multi {
+  std::vector<mm_context *> ctx;
+  std::vector<void **> parts_dev;  // per device: device array of G pointers to the devices' B buffers
+  bool peer = false;
+  std::mutex mutex;
+  // resident problem of the upload / execute / download lifecycle
+  unsigned n = 0, k = 0, m = 0;
+  int dtype = -1;
+};
+
+namespace {
+
+unsigned rows_per_gpu(unsigned n, int g) { return (n + unsigned(g) - 1) / unsigned(g); }
+
+// Runs fn(g) on one host thread per device; returns the first error (message re-set on this thread).
+template <class Fn>
+int fan_out(int gpus, Fn fn) {
+  std::vector<int> rc(gpus, MM_OK);
+  std::vector<std::string> msg(gpus);
+  std::vector<std::thread> pool;
+  for (int g = 0; g < gpus; ++g) {
+    pool.emplace_back([&, g] {
+      rc[g] = fn(g);
+      if (rc[g] != MM_OK) msg[g] = mm_last_error();
+    });
+  }
+  for (auto &t : pool) t.join();
+  for (int g = 0; g < gpus; ++g) {
+    if (rc[g] != MM_OK) return fail(rc[g], "GPU " + std::to_string(g) + ": " + msg[g]);
+  }
+  return MM_OK;
+}
+
+// Point every device's slice table at the devices' current B buffers (they move when they grow).
+int refresh_parts(mm_multi *mu, int g, size_t b_bytes) {
+  mm_context *ctx = mu->ctx[g];
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
+  (void)b_bytes;
+  std::vector<void *> table(mu->ctx.size());
+  for (size_t j = 0; j < mu->ctx.size(); ++j) table[j] = mu->ctx[j]->staging[1].ptr;
+  MM_CUDA_TRY(cudaMemcpy(mu->parts_dev[g], table.data(), table.size() * sizeof(void *), cudaMemcpyHostToDevice));
+  return MM_OK;
+}
+
+int multi_gemm_host_locked(mm_multi *mu, int dtype, int map_op, int reduce_op, int flags, const void *a, const void *b,
+                           void *c, unsigned n, unsigned k, unsigned m, double *seconds_device) {
+  if (flags & MM_FLAG_TRANSPOSED_A) {
+    return fail(MM_ERR_UNSUPPORTED, "the row-block split over GPUs needs row-major A (MM_TRANSPOSED_A is set)");
+  }
+  const int G = int(mu->ctx.size());
+  const size_t es = mm_dtype_size(dtype);
+  const unsigned per = rows_per_gpu(n, G);
+  // B row-slices: multiples of 64 k-rows so that a preparation work item never straddles two GPUs
+  const unsigned part_rows = mu->peer ? std::max(64u, (rows_per_gpu(k, G) + 63u) / 64u * 64u) : k;
+  const unsigned parts = mu->peer ? (k + part_rows - 1) / part_rows : 1;
+  std::vector<Pipeline> pipes(G);
+  std::vector<BPlan> plans(G);
+  std::vector<double> dev_s(G, 0.0);
+  HostBarrier barrier(G);
+  int rc = fan_out(G, [&](int g) -> int {
+    const unsigned r0 = std::min(n, unsigned(g) * per), r1 = std::min(n, r0 + per);
+    Pipeline &p = pipes[g];
+    p = Pipeline{mu->ctx[g], dtype, map_op, reduce_op, flags,
+                 static_cast<const unsigned char *>(a) + size_t(r0) * k * es, static_cast<const unsigned char *>(b),
+                 static_cast<unsigned char *>(c) + size_t(r0) * m * es, r1 - r0, k, m, es,
+                 select_path(dtype, map_op, reduce_op, flags, std::max(1u, r1 - r0))};
+    BPlan &bp = plans[g];
+    if (mu->peer) {
+      bp.k0 = std::min(k, unsigned(g) * part_rows);
+      bp.k1 = std::min(k, bp.k0 + part_rows);
+      if (unsigned(g) >= parts) bp.k0 = bp.k1 = k;  // more GPUs than slices
+      bp.parts = parts;
+      bp.part_rows = part_rows;
+      bp.parts_dev = mu->parts_dev[g];
+    } else {
+      bp.k0 = 0;
+      bp.k1 = k;
+    }
+    std::lock_guard<std::mutex> lock(mu->ctx[g]->mutex);
+    // a GPU without rows still uploads its slice of B: the others read it
+    if (p.rows == 0) p.rows = 1, p.a_host = static_cast<const unsigned char *>(a), p.c_host = nullptr;
+    int rc1 = p.upload_b(bp);
+    barrier.arrive_and_wait();  // every slice event is recorded and every B buffer has its final address
+    int rc2 = (rc1 == MM_OK && mu->peer) ? refresh_parts(mu, g, size_t(k) * m * es) : MM_OK;
+    if (mu->peer) {
+      for (int j = 0; j < G; ++j) {
+        if (j != g) bp.peer_slices.push_back(mu->ctx[j]->ev_slice);
+      }
+    }
+    barrier.arrive_and_wait();  // all slice tables are in place before any kernel dereferences one
+    int rc3 = MM_OK;
+    if (rc1 == MM_OK && rc2 == MM_OK && r1 > r0) {
+      rc3 = p.run(bp, &dev_s[g]);
+    } else {
+      cudaSetDevice(mu->ctx[g]->device);
+      cudaStreamSynchronize(mu->ctx[g]->copy_in);
+    }
+    // nobody's B buffer may be reused (next call) before every peer has finished reading it
+    barrier.arrive_and_wait();
+    return rc1 != MM_OK ? rc1 : (rc2 != MM_OK ? rc2 : rc3);
+  });
+  if (rc != MM_OK) return rc;
+  if (seconds_device) *seconds_device = *std::max_element(dev_s.begin(), dev_s.end());
+  return MM_OK;
+}
+
+int create_multi(int n_gpus, const int *devices, mm_multi **out) {
+  mm_multi *mu = new mm_multi();
+  auto cleanup = [&](int rc) {
+    const std::string msg = mm_last_error();
+    mm_multi_destroy(mu);
+    mm::set_error(msg);
+    return rc;
+  };
+  for (int g = 0; g < n_gpus; ++g) {
+    mm_context *c = nullptr;
+    const int rc = mm_context_create(devices ? devices[g] : g, &c);
+    if (rc != MM_OK) return cleanup(rc);
+    mu->ctx.push_back(c);
+  }
+  mu->peer = n_gpus > 1;
+  for (int g = 0; g < n_gpus && mu->peer; ++g) {
+    for (int j = 0; j < n_gpus; ++j) {
+      if (mu->ctx[j]->device == mu->ctx[g]->device) continue;  // the same device twice (tests): plain local memory
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, mu->ctx[g]->device, mu->ctx[j]->device) != cudaSuccess || !can) mu->peer = false;
+    }
+  }
+  for (int g = 0; g < n_gpus; ++g) {
+    if (cudaSetDevice(mu->ctx[g]->device) != cudaSuccess) return cleanup(fail(MM_ERR_CUDA, "cudaSetDevice failed"));
+    for (int j = 0; j < n_gpus && mu->peer; ++j) {
+      if (mu->ctx[j]->device == mu->ctx[g]->device) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(mu->ctx[j]->device, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) mu->peer = false;
+    }
+    void **table = nullptr;
+    if (cudaMalloc(&table, sizeof(void *) * size_t(n_gpus)) != cudaSuccess) {
+      return cleanup(fail(MM_ERR_NOMEM, "cudaMalloc of the slice table failed"));
+    }
+    mu->parts_dev.push_back(table);
+  }
+  *out = mu;
+  return MM_OK;
+}
 
 }  // namespace
 
@@ -140,7 +606,7 @@ extern "C" {
 
 const char *mm_last_error(void) { return mm::g_last_error.c_str(); }
 
-int mm_version(void) { return 100; }
+int mm_version(void) { return 200; }
 
 size_t mm_dtype_size(int dtype) {
   switch (dtype) {
@@ -178,32 +644,49 @@ int mm_context_create(int device, mm_context **out) {
   }
   mm_context *ctx = new mm_context();
   ctx->device = device;
-  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
-  MM_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-  MM_CUDA_TRY(cudaEventCreate(&ctx->ev_start));
-  MM_CUDA_TRY(cudaEventCreate(&ctx->ev_stop));
+  ctx->tuning = mm::default_tuning();
+  const int rc = init_context(ctx);
+  if (rc != MM_OK) {
+    const std::string msg = mm_last_error();
+    destroy_context(ctx);  // releases whatever was created before the failure
+    mm::set_error(msg);
+    return rc;
+  }
   *out = ctx;
   return MM_OK;
 }
 
 int mm_context_destroy(mm_context *ctx) {
   if (!ctx) return MM_OK;
-  cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  if (ctx->scratch.ptr) cudaFree(ctx->scratch.ptr);
-  for (auto &s : ctx->staging) {
-    if (s.ptr) cudaFree(s.ptr);
-  }
-  for (auto e : ctx->prof_events) cudaEventDestroy(e);
-  for (auto e : ctx->sync_events) cudaEventDestroy(e);
-  cudaStreamDestroy(ctx->copy_in);
-  cudaStreamDestroy(ctx->copy_out);
-  cudaEventDestroy(ctx->ev_start);
-  cudaEventDestroy(ctx->ev_stop);
-  cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  destroy_context(ctx);
   return MM_OK;
+}
+
+int mm_context_set_tuning(mm_context *ctx, int knob, int value) {
+  if (!ctx) return fail(MM_ERR_INVALID, "null context");
+  const int rc = mm::tuning_validate(knob, value);
+  if (rc != MM_OK) return rc;
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  ctx->tuning.v[knob] = value;
+  return MM_OK;
+}
+
+int mm_context_get_tuning(mm_context *ctx, int knob, int *value) {
+  if (!ctx || !value) return fail(MM_ERR_INVALID, "null argument");
+  if (knob < 0 || knob >= MM_TUNE_COUNT) return fail(MM_ERR_INVALID, "unknown tuning knob " + std::to_string(knob));
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  *value = ctx->tuning.v[knob];
+  return MM_OK;
+}
+
+int mm_context_reserve(mm_context *ctx, int dtype, int flags, unsigned n, unsigned k, unsigned m) {
+  if (!ctx) return fail(MM_ERR_INVALID, "null context");
+  if (!valid_dtype(dtype)) return fail(MM_ERR_INVALID, "unknown MM_DATA_TYPE code");
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  MM_CUDA_TRY(cudaSetDevice(ctx->device));
+  if (dtype != MM_DTYPE_FLOAT && dtype != MM_DTYPE_HALF) return MM_OK;  // only the tcgen05 path keeps scratch
+  return ensure(ctx, ctx->scratch, mm::tcgen05_scratch_bytes(dtype, n, k, m, flags & ~MM_FLAG_EXACT, ctx->tuning),
+                ctx->captured);
 }
 
 int mm_buffer_alloc(mm_context *ctx, size_t bytes, void **device_ptr) {
@@ -249,6 +732,7 @@ int mm_kernel_enqueue(mm_context *ctx, int dtype, int map_op, int reduce_op, int
   if (!ctx) return fail(MM_ERR_INVALID, "null context");
   int rc = check_args(dtype, map_op, reduce_op, a, b, c, n, k, m);
   if (rc != MM_OK) return rc;
+  if ((rc = check_device_alignment(a, b, c)) != MM_OK) return rc;
   std::lock_guard<std::mutex> lock(ctx->mutex);
   MM_CUDA_TRY(cudaSetDevice(ctx->device));
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
@@ -261,6 +745,7 @@ int mm_kernel_execute(mm_context *ctx, int dtype, int map_op, int reduce_op, int
   if (!ctx) return fail(MM_ERR_INVALID, "null context");
   int rc = check_args(dtype, map_op, reduce_op, a, b, c, n, k, m);
   if (rc != MM_OK) return rc;
+  if ((rc = check_device_alignment(a, b, c)) != MM_OK) return rc;
   std::lock_guard<std::mutex> lock(ctx->mutex);
   MM_CUDA_TRY(cudaSetDevice(ctx->device));
   // allocate scratch / load kernels first: the device time below is kernel time only, like the
@@ -270,7 +755,10 @@ int mm_kernel_execute(mm_context *ctx, int dtype, int map_op, int reduce_op, int
   const auto t0 = std::chrono::high_resolution_clock::now();
   MM_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
   rc = enqueue_locked(ctx, dtype, map_op, reduce_op, flags, a, b, c, n, k, m, ctx->stream);
-  if (rc != MM_OK) return rc;
+  if (rc != MM_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+  }
   MM_CUDA_TRY(cudaEventRecord(ctx->ev_stop, ctx->stream));
   MM_CUDA_TRY(cudaEventSynchronize(ctx->ev_stop));
   const auto t1 = std::chrono::high_resolution_clock::now();
@@ -312,10 +800,11 @@ int mm_context_profile_read(mm_context *ctx, double *prep_sum, double *main_sum,
 
 int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags) {
   if (!valid_dtype(dtype) || !valid_op(map_op) || !valid_op(reduce_op)) return -1;
-  switch (select_path(dtype, map_op, reduce_op, flags)) {
+  const mm::Tuning t = mm::default_tuning();
+  switch (select_path(dtype, map_op, reduce_op, flags, 2)) {
     case kPathTcgen05:
-      // [B^T prep unless B is read directly] + [A prep for float or transposed A] + GEMM
-      return 1 + (mm::tcgen05_b_direct(dtype) ? 0 : 1) +
+      // [B preparation unless B is read in place] + [A preparation for float or transposed A] + GEMM
+      return 1 + (mm::tcgen05_b_in_place(dtype, flags, t) ? 0 : 1) +
              ((dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) ? 1 : 0);
     case kPathDmma: return 1;
     case kPathSemiring: return 1;
@@ -325,7 +814,7 @@ int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags) {
 
 const char *mm_kernel_path(int dtype, int map_op, int reduce_op, int flags) {
   if (!valid_dtype(dtype) || !valid_op(map_op) || !valid_op(reduce_op)) return "invalid";
-  switch (select_path(dtype, map_op, reduce_op, flags)) {
+  switch (select_path(dtype, map_op, reduce_op, flags, 2)) {
     case kPathTcgen05: return dtype == MM_DTYPE_FLOAT ? "tcgen05_tf32" : "tcgen05_f16";
     case kPathDmma: return "dmma_f64";
     case kPathSemiring: return "semiring_simt";
@@ -340,123 +829,221 @@ int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flag
   if (rc != MM_OK) return rc;
   if (!ctx) {
     std::lock_guard<std::mutex> lock(g_default_mutex);
-    if (!g_default_ctx) {
-      rc = mm_context_create(0, &g_default_ctx);
+    const int gpus = env_int("MM_NUM_GPUS", 1);
+    if (gpus > 1 && !(flags & MM_FLAG_TRANSPOSED_A)) {
+      if (!g_default_multi) {
+        rc = mm_multi_create(gpus, nullptr, &g_default_multi);
+        if (rc != MM_OK) return rc;
+      }
+    } else if (!g_default_ctx) {
+      rc = mm_context_create(env_int("MM_DEVICE", 0), &g_default_ctx);
       if (rc != MM_OK) return rc;
+    }
+    if (gpus > 1 && !(flags & MM_FLAG_TRANSPOSED_A)) {
+      return mm_multi_gemm_host(g_default_multi, dtype, map_op, reduce_op, flags, a, b, c, n, k, m, seconds_device,
+                                seconds_wall);
     }
     ctx = g_default_ctx;
   }
   const auto t0 = std::chrono::high_resolution_clock::now();
   std::lock_guard<std::mutex> lock(ctx->mutex);
-  MM_CUDA_TRY(cudaSetDevice(ctx->device));
-  const size_t es = mm_dtype_size(dtype);
-  const size_t bytes_a = size_t(n) * k * es, bytes_b = size_t(k) * m * es, bytes_c = size_t(n) * m * es;
-  if ((rc = ensure(ctx->staging[0], bytes_a)) != MM_OK) return rc;
-  if ((rc = ensure(ctx->staging[1], bytes_b)) != MM_OK) return rc;
-  if ((rc = ensure(ctx->staging[2], bytes_c)) != MM_OK) return rc;
-  unsigned char *da = static_cast<unsigned char *>(ctx->staging[0].ptr);
-  unsigned char *db = static_cast<unsigned char *>(ctx->staging[1].ptr);
-  unsigned char *dc = static_cast<unsigned char *>(ctx->staging[2].ptr);
-  const unsigned char *ha = static_cast<const unsigned char *>(a);
-  unsigned char *hc = static_cast<unsigned char *>(c);
-
-  // Row-chunk pipeline: C row-blocks are independent (kernel/Compute.cpp:53-56), so the H2D copy of
-  // A chunk i+1, the kernels of chunk i and the D2H copy of C chunk i-1 run concurrently on three
-  // streams; B is copied (and, on the tcgen05 path, prepared) once up front.  A stored K x N cannot
-  // be cut into contiguous row chunks: it takes the single-chunk route.
-  Path path = select_path(dtype, map_op, reduce_op, flags);
-  const bool ta = (flags & MM_FLAG_TRANSPOSED_A) != 0;
-  if (path == kPathDmma && ta && (n % 2 != 0)) path = kPathSemiring;
-  unsigned chunk_rows = n;
-  if (!ta) {
-    const size_t row_bytes = size_t(k) * es;
-    size_t rows = std::max<size_t>((n + 15) / 16, ((size_t(32) << 20) + row_bytes - 1) / row_bytes);
-    rows = (rows + 127) / 128 * 128;
-    if (rows < n) chunk_rows = unsigned(rows);
+  Pipeline p{ctx, dtype, map_op, reduce_op, flags, static_cast<const unsigned char *>(a),
+             static_cast<const unsigned char *>(b), static_cast<unsigned char *>(c), n, k, m, mm_dtype_size(dtype),
+             select_path(dtype, map_op, reduce_op, flags, n)};
+  BPlan bp;
+  bp.k0 = 0;
+  bp.k1 = k;
+  rc = p.upload_b(bp);
+  if (rc == MM_OK) {
+    rc = p.run(bp, seconds_device);
+  } else {
+    cudaStreamSynchronize(ctx->copy_in);
   }
-  const unsigned chunks = (n + chunk_rows - 1) / chunk_rows;
-  while (ctx->sync_events.size() < size_t(2 * chunks + 1)) {
-    cudaEvent_t e;
-    MM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ctx->sync_events.push_back(e);
-  }
-  cudaEvent_t ev_b = ctx->sync_events[0];
-  auto ev_a = [&](unsigned i) { return ctx->sync_events[1 + i]; };
-  auto ev_c = [&](unsigned i) { return ctx->sync_events[1 + chunks + i]; };
-
-  // ---- H2D stream
-  MM_CUDA_TRY(cudaMemcpyAsync(db, b, bytes_b, cudaMemcpyHostToDevice, ctx->copy_in));
-  MM_CUDA_TRY(cudaEventRecord(ev_b, ctx->copy_in));
-  for (unsigned i = 0; i < chunks; ++i) {
-    const size_t r0 = size_t(i) * chunk_rows, rows = std::min<size_t>(chunk_rows, n - r0);
-    if (!ta) {
-      MM_CUDA_TRY(cudaMemcpyAsync(da + r0 * k * es, ha + r0 * k * es, rows * k * es, cudaMemcpyHostToDevice,
-                                  ctx->copy_in));
-    } else {
-      MM_CUDA_TRY(cudaMemcpyAsync(da, ha, bytes_a, cudaMemcpyHostToDevice, ctx->copy_in));
-    }
-    MM_CUDA_TRY(cudaEventRecord(ev_a(i), ctx->copy_in));
-  }
-
-  // ---- compute stream
-  void *bt = nullptr;
-  unsigned char *aprep = nullptr;
-  if (path == kPathTcgen05) {
-    if ((rc = ensure(ctx->scratch, mm::tcgen05_scratch_bytes(dtype, n, k, m, flags))) != MM_OK) return rc;
-    bt = ctx->scratch.ptr;
-    aprep = static_cast<unsigned char *>(ctx->scratch.ptr) + mm::tcgen05_bt_bytes(dtype, k, m, flags);
-  }
-  MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev_b, 0));
-  MM_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
-  const void *b_op = nullptr;
-  if (path == kPathTcgen05) {
-    if ((rc = mm::tcgen05_prepare_b(dtype, db, bt, k, m, flags, &b_op, ctx->stream)) != MM_OK) return rc;
-  }
-  for (unsigned i = 0; i < chunks; ++i) {
-    const size_t r0 = size_t(i) * chunk_rows, rows = std::min<size_t>(chunk_rows, n - r0);
-    MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev_a(i), 0));
-    const void *a_chunk = da + (ta ? 0 : r0 * k * es);
-    void *c_chunk = dc + r0 * m * es;
-    if (path == kPathTcgen05) {
-      const void *a_op = nullptr, *a_raw = nullptr;
-      const size_t a_scale = (dtype == MM_DTYPE_FLOAT && (flags & MM_FLAG_TF32X3)) ? 3 : 1;
-      rc = mm::tcgen05_prepare_a(dtype, a_chunk, aprep + (ta ? 0 : r0 * k * es * a_scale), unsigned(rows), k, flags,
-                                 &a_op, &a_raw, ctx->stream);
-      if (rc != MM_OK) return rc;
-      unsigned char *tail = static_cast<unsigned char *>(ctx->scratch.ptr) + ctx->scratch.bytes;
-      unsigned int *tile_sync = reinterpret_cast<unsigned int *>(tail - 256);
-      unsigned int *a_done = reinterpret_cast<unsigned int *>(tail - mm::kTcgen05TailBytes);
-      rc = mm::tcgen05_gemm(dtype, a_op, b_op, c_chunk, unsigned(rows), k, m, flags, tile_sync, a_raw, a_done,
-                            ctx->stream);
-    } else {
-      mm::GemmArgs g{a_chunk, db, c_chunk, unsigned(rows), k, m, flags, ctx->stream};
-      rc = (path == kPathDmma) ? mm::launch_dmma(g) : mm::launch_semiring(dtype, map_op, reduce_op, g);
-    }
-    if (rc != MM_OK) return rc;
-    MM_CUDA_TRY(cudaEventRecord(ev_c(i), ctx->stream));
-  }
-  MM_CUDA_TRY(cudaEventRecord(ctx->ev_stop, ctx->stream));
-
-  // ---- D2H stream
-  for (unsigned i = 0; i < chunks; ++i) {
-    const size_t r0 = size_t(i) * chunk_rows, rows = std::min<size_t>(chunk_rows, n - r0);
-    MM_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ev_c(i), 0));
-    MM_CUDA_TRY(cudaMemcpyAsync(hc + r0 * m * es, dc + r0 * m * es, rows * m * es, cudaMemcpyDeviceToHost,
-                                ctx->copy_out));
-  }
-  MM_CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
-  MM_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (seconds_device) {
-    // first kernel start .. last kernel end on the compute stream (with more than one chunk this
-    // includes the stalls waiting for A chunks to arrive)
-    float ms = 0.f;
-    MM_CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop));
-    *seconds_device = 1e-3 * ms;
-  }
+  if (rc != MM_OK) return rc;
   if (seconds_wall) {
     *seconds_wall = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
   }
   return MM_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------
+
+int mm_multi_create(int n_gpus, const int *devices, mm_multi **out) {
+  if (!out) return fail(MM_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  if (n_gpus < 1) return fail(MM_ERR_INVALID, "mm_multi_create needs at least one device");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    return fail(MM_ERR_CUDA, std::string("no CUDA device available: ") +
+                                 (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  }
+  if (n_gpus > count) {
+    return fail(MM_ERR_INVALID, "mm_multi_create: " + std::to_string(n_gpus) + " devices requested, " +
+                                    std::to_string(count) + " visible");
+  }
+  return create_multi(n_gpus, devices, out);
+}
+
+int mm_multi_destroy(mm_multi *mu) {
+  if (!mu) return MM_OK;
+  for (size_t g = 0; g < mu->ctx.size(); ++g) {
+    if (g < mu->parts_dev.size() && mu->parts_dev[g]) {
+      cudaSetDevice(mu->ctx[g]->device);
+      cudaFree(mu->parts_dev[g]);
+    }
+  }
+  for (mm_context *c : mu->ctx) destroy_context(c);
+  delete mu;
+  return MM_OK;
+}
+
+int mm_multi_device_count(const mm_multi *mu) { return mu ? int(mu->ctx.size()) : 0; }
+
+mm_context *mm_multi_context(mm_multi *mu, int index) {
+  if (!mu || index < 0 || index >= int(mu->ctx.size())) return nullptr;
+  return mu->ctx[index];
+}
+
+int mm_multi_peer_access(const mm_multi *mu) { return (mu && mu->peer) ? 1 : 0; }
+
+int mm_multi_gemm_host(mm_multi *mu, int dtype, int map_op, int reduce_op, int flags, const void *a, const void *b,
+                       void *c, unsigned n, unsigned k, unsigned m, double *seconds_device, double *seconds_wall) {
+  if (!mu) return fail(MM_ERR_INVALID, "null multi-GPU context");
+  int rc = check_args(dtype, map_op, reduce_op, a, b, c, n, k, m);
+  if (rc != MM_OK) return rc;
+  const auto t0 = std::chrono::high_resolution_clock::now();
+  std::lock_guard<std::mutex> lock(mu->mutex);
+  rc = multi_gemm_host_locked(mu, dtype, map_op, reduce_op, flags, a, b, c, n, k, m, seconds_device);
+  if (rc != MM_OK) return rc;
+  if (seconds_wall) {
+    *seconds_wall = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+  }
+  return MM_OK;
+}
+
+int mm_multi_upload(mm_multi *mu, int dtype, int flags, const void *a, const void *b, unsigned n, unsigned k,
+                    unsigned m) {
+  if (!mu) return fail(MM_ERR_INVALID, "null multi-GPU context");
+  int rc = check_args(dtype, MM_OP_MULTIPLY, MM_OP_ADD, a, b, a /*non-null placeholder*/, n, k, m);
+  if (rc != MM_OK) return rc;
+  if (flags & MM_FLAG_TRANSPOSED_A) {
+    return fail(MM_ERR_UNSUPPORTED, "the row-block split over GPUs needs row-major A (MM_TRANSPOSED_A is set)");
+  }
+  std::lock_guard<std::mutex> lock(mu->mutex);
+  const int G = int(mu->ctx.size());
+  const size_t es = mm_dtype_size(dtype);
+  const unsigned per = rows_per_gpu(n, G);
+  const unsigned part_rows = mu->peer ? std::max(64u, (rows_per_gpu(k, G) + 63u) / 64u * 64u) : k;
+  const unsigned parts = mu->peer ? (k + part_rows - 1) / part_rows : 1;
+  HostBarrier barrier(G);
+  rc = fan_out(G, [&](int g) -> int {
+    mm_context *ctx = mu->ctx[g];
+    std::lock_guard<std::mutex> ctx_lock(ctx->mutex);
+    const unsigned r0 = std::min(n, unsigned(g) * per), r1 = std::min(n, r0 + per);
+    const unsigned rows = std::max(1u, r1 - r0);
+    auto body = [&]() -> int {
+      MM_CUDA_TRY(cudaSetDevice(ctx->device));
+      int r;
+      if ((r = ensure(ctx, ctx->staging[0], size_t(rows) * k * es, false)) != MM_OK) return r;
+      if ((r = ensure(ctx, ctx->staging[1], size_t(k) * m * es, false)) != MM_OK) return r;
+      if ((r = ensure(ctx, ctx->staging[2], size_t(rows) * m * es, false)) != MM_OK) return r;
+      unsigned char *db = static_cast<unsigned char *>(ctx->staging[1].ptr);
+      unsigned k0 = 0, k1 = k;
+      if (mu->peer) {
+        k0 = std::min(k, unsigned(g) * part_rows);
+        k1 = (unsigned(g) >= parts) ? k0 : std::min(k, k0 + part_rows);
+      }
+      const size_t off = size_t(k0) * m * es;
+      if (k1 > k0) {
+        MM_CUDA_TRY(cudaMemcpyAsync(db + off, static_cast<const unsigned char *>(b) + off, size_t(k1 - k0) * m * es,
+                                    cudaMemcpyHostToDevice, ctx->copy_in));
+      }
+      MM_CUDA_TRY(cudaEventRecord(ctx->ev_slice, ctx->copy_in));
+      if (r1 > r0) {
+        MM_CUDA_TRY(cudaMemcpyAsync(ctx->staging[0].ptr, static_cast<const unsigned char *>(a) + size_t(r0) * k * es,
+                                    size_t(r1 - r0) * k * es, cudaMemcpyHostToDevice, ctx->copy_in));
+      }
+      return MM_OK;
+    };
+    const int rc1 = body();
+    barrier.arrive_and_wait();
+    int rc2 = MM_OK;
+    if (rc1 == MM_OK && mu->peer) {
+      rc2 = refresh_parts(mu, g, 0);
+    }
+    barrier.arrive_and_wait();
+    if (rc1 == MM_OK && rc2 == MM_OK && mu->peer) {
+      auto gather = [&]() -> int {
+        MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_slice, 0));
+        for (int j = 0; j < G; ++j) {
+          if (j != g) MM_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, mu->ctx[j]->ev_slice, 0));
+        }
+        mm::BSource src;
+        src.src = mu->parts_dev[g];
+        src.parts = parts;
+        src.part_rows = part_rows;
+        return mm::gather_b_rows(src, ctx->staging[1].ptr, es, k, m, ctx->stream);
+      };
+      rc2 = gather();
+    }
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->copy_in);
+    cudaStreamSynchronize(ctx->stream);
+    barrier.arrive_and_wait();
+    return rc1 != MM_OK ? rc1 : rc2;
+  });
+  if (rc != MM_OK) return rc;
+  mu->n = n;
+  mu->k = k;
+  mu->m = m;
+  mu->dtype = dtype;
+  return MM_OK;
+}
+
+int mm_multi_execute(mm_multi *mu, int dtype, int map_op, int reduce_op, int flags, unsigned n, unsigned k, unsigned m,
+                     double *seconds_device, double *seconds_wall) {
+  if (!mu) return fail(MM_ERR_INVALID, "null multi-GPU context");
+  if (!valid_dtype(dtype) || !valid_op(map_op) || !valid_op(reduce_op)) return fail(MM_ERR_INVALID, "unknown type / operator code");
+  std::lock_guard<std::mutex> lock(mu->mutex);
+  if (mu->dtype != dtype || mu->n != n || mu->k != k || mu->m != m) {
+    return fail(MM_ERR_INVALID, "mm_multi_execute: no matching mm_multi_upload (type or sizes differ)");
+  }
+  const int G = int(mu->ctx.size());
+  const unsigned per = rows_per_gpu(n, G);
+  std::vector<double> dev_s(G, 0.0);
+  const auto t0 = std::chrono::high_resolution_clock::now();
+  int rc = fan_out(G, [&](int g) -> int {
+    const unsigned r0 = std::min(n, unsigned(g) * per), r1 = std::min(n, r0 + per);
+    if (r1 == r0) return MM_OK;
+    mm_context *ctx = mu->ctx[g];
+    return mm_kernel_execute(ctx, dtype, map_op, reduce_op, flags, ctx->staging[0].ptr, ctx->staging[1].ptr,
+                             ctx->staging[2].ptr, r1 - r0, k, m, &dev_s[g], nullptr);
+  });
+  if (rc != MM_OK) return rc;
+  if (seconds_device) *seconds_device = *std::max_element(dev_s.begin(), dev_s.end());
+  if (seconds_wall) {
+    *seconds_wall = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+  }
+  return MM_OK;
+}
+
+int mm_multi_download(mm_multi *mu, int dtype, void *c, unsigned n, unsigned m) {
+  if (!mu || !c) return fail(MM_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lock(mu->mutex);
+  if (mu->dtype != dtype || mu->n != n || mu->m != m) {
+    return fail(MM_ERR_INVALID, "mm_multi_download: no matching mm_multi_upload (type or sizes differ)");
+  }
+  const int G = int(mu->ctx.size());
+  const size_t es = mm_dtype_size(dtype);
+  const unsigned per = rows_per_gpu(n, G);
+  return fan_out(G, [&](int g) -> int {
+    const unsigned r0 = std::min(n, unsigned(g) * per), r1 = std::min(n, r0 + per);
+    if (r1 == r0) return MM_OK;
+    mm_context *ctx = mu->ctx[g];
+    return mm_copy_to_host(ctx, static_cast<unsigned char *>(c) + size_t(r0) * m * es, ctx->staging[2].ptr,
+                           size_t(r1 - r0) * m * es);
+  });
 }
 
 }  // extern "C"

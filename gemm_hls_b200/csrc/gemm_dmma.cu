@@ -216,16 +216,13 @@ int launch_dmma(const GemmArgs &g) {
   // (e.g. a 1024-row block of the 8-GPU split of 8192^3: 512 tiles on 148 SMs = 3.46 waves; 1024
   // half-height tiles = 6.92 waves of half the duration).  The half-height tile reads B twice as
   // often per output row and runs ~2 % below the full tile, so it has to win by more than 5 %.
-  // MM_DMMA_TILE_ROWS=64|128 forces one of them.
+  // The tuning knob MM_TUNE_DMMA_TILE_ROWS (64 | 128) forces one of them.
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const double t128 = double(ceil_div(g.n, 128)) * ceil_div(g.m, BN), t64 = double(ceil_div(g.n, 64)) * ceil_div(g.m, BN);
   const double cost128 = std::ceil(t128 / sms), cost64 = 0.5 * 1.05 * std::ceil(t64 / sms);
-  static const int forced = [] {
-    const char *e = std::getenv("MM_DMMA_TILE_ROWS");
-    return e ? std::atoi(e) : 0;
-  }();
+  const int forced = g.tuning ? g.tuning->dmma_tile_rows() : 0;
   const bool use64 = forced == 64 || (forced != 128 && cost64 < cost128);
   return use64 ? launch_dmma_tma<64>(g) : launch_dmma_tma<128>(g);
 }

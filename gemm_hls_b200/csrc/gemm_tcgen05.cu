@@ -4,29 +4,36 @@
 // kernel/Memory.cpp:58-438) for MM_MAP_OP=Multiply, MM_REDUCE_OP=Add, MM_DATA_TYPE in {float, half}.
 //
 // Structure (one persistent CTA per SM, warp-specialised, no CUTLASS):
-//   warp 0   TMA producer: cp.async.bulk.tensor 128-byte-swizzled A (128 x BK) and B^T (256 x BK)
-//            tiles into a STAGES-deep shared-memory ring, mbarrier full/empty pairs
-//   warp 1   MMA issuer: one thread issues tcgen05.mma (kind::tf32 | kind::f16, M=128, N=256,
-//            K=32 bytes) into one of two 256-column FP32 accumulators in TMEM; tcgen05.commit
+//   warp 0   TMA producer (the role of ReadA / ReadB / FeedB): cp.async.bulk.tensor of 128-byte-swizzled
+//            A (128 x BK, K-major) and B tiles into a STAGES-deep shared-memory ring, mbarrier full/empty
+//            pairs.  B is read MN-major STRAIGHT from the reference's row-major K x M layout (boxes of
+//            one swizzle atom of columns x BK k-rows), or K-major from a transposed copy (tuning knob).
+//   warp 1   MMA issuer (the PE chain): one thread issues tcgen05.mma (kind::tf32 | kind::f16, M = 128 per
+//            CTA, N = 128 | 256, K = 32 bytes) into one of two FP32 accumulators in TMEM; tcgen05.commit
 //            releases smem stages and publishes finished accumulators
-//   warps 2-5 epilogue: tcgen05.ld the accumulator (each warp its 32-lane TMEM quarter), convert,
-//            predicated 128-bit stores of the C tile (n < N, m < M masking = WriteC,
-//            kernel/Memory.cpp:378-381); overlaps the next tile's main loop (double-buffered TMEM)
+//   warps 2-5 epilogue (WriteC, kernel/Memory.cpp:361-392): tcgen05.ld the accumulator (each warp its
+//            32-lane TMEM quarter), convert, stage 32 x 32 blocks in swizzled shared memory and write
+//            them with TMA stores (cp.async.bulk.tensor, clipped to n < N, m < M by the tensor map);
+//            overlaps the next tile's main loop (double-buffered TMEM)
 //
-// Operand preparation (prep kernels below; O(N*K + K*M) bytes against O(N*K*M) flops):
+// Operand preparation (O(N*K + K*M) bytes against O(N*K*M) flops):
 //   * kind::tf32 reads only the upper 19 bits of each fp32 operand, i.e. it TRUNCATES.  The
 //     reference's inputs are all positive (U[1,10], test/TestSimulation.cpp:46-55), so truncation
 //     would bias every product by about -2^-11 * 2 and land the sum right at the 1e-3 tolerance.
-//     A and B are therefore rounded to nearest TF32 (cvt.rna.tf32.f32) first.
-//   * both MMA operands are consumed K-major, so B (row-major K x M) is transposed to M x K in the
-//     same pass that rounds it (for half: transposed only); A (row-major N x K) is K-major already.
+//     A and B are therefore rounded to nearest TF32 (cvt.rna.tf32.f32) into scratch copies first.
+//   * B's rounding runs CONCURRENTLY with the GEMM: a co-resident persistent kernel on a second
+//     stream rounds B panel by panel (BLOCK_N columns x all of K, in the order the rasterisation
+//     consumes panels) and publishes each panel through a counter; the GEMM's producer waits for a
+//     panel's counter before its first TMA load from it.  The same pass can read row-slices of B
+//     from PEER GPUs (multi-GPU host path): the NVLink all-gather of B is fused into it.
+//   * half needs no preparation at all: A is K-major as stored, B is read MN-major in place.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdlib>
-#include <mutex>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -37,31 +44,32 @@ namespace mm {
 namespace {
 
 constexpr int BLOCK_M = 128;          // C rows per CTA      (UMMA M = 128 * CTA group size)
-constexpr int BLOCK_N = 256;          // C cols per tile     (UMMA N)
 constexpr int BLOCK_K_BYTES = 128;    // one 128-byte swizzle atom of K per stage
 constexpr int UMMA_K_BYTES = 32;      // K extent of one tcgen05.mma
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
 constexpr int NUM_THREADS = 192;
-constexpr int MN_ATOM = 64;                       // elements of N per MN-major swizzle atom (128 B of f16)
-constexpr int MN_ATOM_BYTES = 64 * BLOCK_K_BYTES; // one atom: BLOCK_K (= 64 for f16) k-rows x 128 B
-constexpr int RASTER_GROUP_ROWS = 2048;  // C rows per rasterisation group (L2 reuse of B^T panels)
+constexpr int EPI_BUF_BYTES = 4096;   // one 32 x 32 fp32 block per epilogue warp
+constexpr int EPI_BYTES = 4 * EPI_BUF_BYTES;
+constexpr int BAR_BYTES = 256;
+constexpr int MAX_DYN_SMEM = 232448;  // 227 KiB per CTA on sm_100a
 
-// Per-variant geometry.  CG = 1: one CTA computes a 128 x 256 tile and stages A (128 rows) + B^T
-// (256 rows) per k-block.  CG = 2 (cta_group::2): a CTA PAIR computes 256 x 256 with ONE
-// tcgen05.mma per k-step issued by the leader CTA; each CTA stages only its own 128 A rows and its
-// half (128 rows) of the B^T tile, so per-SM shared-memory fill and L2 traffic drop by a third and
-// the freed shared memory deepens the ring from 4 to 6 stages.
-template <int CG>
+// Per-variant geometry.  CG = 1: one CTA computes a 128 x BN tile and stages A (128 rows) + all BN
+// columns of B per k-block.  CG = 2 (cta_group::2): a CTA PAIR computes 256 x BN with ONE tcgen05.mma
+// per k-step issued by the leader CTA; each CTA stages only its own 128 A rows and its half of the B
+// tile, so per-SM shared-memory fill and L2 traffic drop and the freed memory deepens the ring.
+template <int CG, int BN>
 struct Geo {
-  static constexpr int LOAD_N = BLOCK_N / CG;                       // B^T rows staged per CTA
+  static constexpr int LOAD_N = BN / CG;                            // B columns staged per CTA
   static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K_BYTES;     // 16 KiB
-  static constexpr int B_STAGE_BYTES = LOAD_N * BLOCK_K_BYTES;      // 32 / 16 KiB
+  static constexpr int B_STAGE_BYTES = LOAD_N * BLOCK_K_BYTES;      // 8 .. 32 KiB
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (CG == 1) ? 4 : 6;
+  static constexpr int FIT = (MAX_DYN_SMEM - 1024 - BAR_BYTES - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int MAX_STAGES = FIT < 8 ? FIT : 8;              // 6 (2,256)  4 (1,256)  8 (2,128)  6 (1,128)
   static constexpr int TILE_ROWS = BLOCK_M * CG;                    // C rows per CTA group
-  static constexpr int RASTER_GROUP = RASTER_GROUP_ROWS / TILE_ROWS;
-  static constexpr size_t SMEM_BYTES = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = ACC_STAGES * BN;                 // 512 | 256
+  static constexpr size_t smem_bytes(int stages) {
+    return size_t(stages) * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + BAR_BYTES;
+  }
 };
 
 struct TileCoord {
@@ -69,7 +77,8 @@ struct TileCoord {
 };
 
 // Grouped rasterisation: RASTER_GROUP row-tiles sweep all column-tiles together so that the
-// concurrently running tiles share A row-panels and B column-panels through L2.
+// concurrently running tiles share A row-panels and B column-panels through L2.  Column tiles are
+// visited in ascending order within a group — the order B's preparation publishes its panels in.
 __device__ __forceinline__ TileCoord tile_coord(uint32_t t, uint32_t tiles_r, uint32_t tiles_c,
                                                 uint32_t raster_group) {
   const uint32_t per_group = raster_group * tiles_c;
@@ -80,13 +89,14 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, uint32_t tiles_r, ui
   return TileCoord{first + in % gsize, in / gsize};
 }
 
+// ---- epilogue stores ------------------------------------------------------------------------------
+// Direct variant (tuning knob tma_store = 0): each lane owns one C row of the chunk.
 template <typename TOut>
-__device__ __forceinline__ void store_chunk(TOut *crow, const uint32_t (&v)[32], uint32_t col,
-                                            uint32_t cols);
+__device__ __forceinline__ void store_chunk(TOut *crow, const uint32_t (&v)[32], uint32_t col, uint32_t cols);
 
 template <>
-__device__ __forceinline__ void store_chunk<float>(float *crow, const uint32_t (&v)[32],
-                                                   uint32_t col, uint32_t cols) {
+__device__ __forceinline__ void store_chunk<float>(float *crow, const uint32_t (&v)[32], uint32_t col,
+                                                   uint32_t cols) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     if (col + j + 4 <= cols) {
@@ -95,20 +105,51 @@ __device__ __forceinline__ void store_chunk<float>(float *crow, const uint32_t (
   }
 }
 
+__device__ __forceinline__ void pack_half(const uint32_t (&v)[32], uint32_t (&p)[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    __half2 h = __floats2half2_rn(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+    p[q] = *reinterpret_cast<uint32_t *>(&h);
+  }
+}
+
 template <>
-__device__ __forceinline__ void store_chunk<__half>(__half *crow, const uint32_t (&v)[32],
-                                                    uint32_t col, uint32_t cols) {
+__device__ __forceinline__ void store_chunk<__half>(__half *crow, const uint32_t (&v)[32], uint32_t col,
+                                                    uint32_t cols) {
+  uint32_t p[16];
+  pack_half(v, p);
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    if (col + j + 8 <= cols) {
-      uint32_t p[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        __half2 h = __floats2half2_rn(__uint_as_float(v[j + 2 * q]), __uint_as_float(v[j + 2 * q + 1]));
-        p[q] = *reinterpret_cast<uint32_t *>(&h);
-      }
-      *reinterpret_cast<uint4 *>(crow + col + j) = make_uint4(p[0], p[1], p[2], p[3]);
+  for (int j = 0; j < 4; ++j) {
+    if (col + 8 * j + 8 <= cols) {
+      *reinterpret_cast<uint4 *>(crow + col + 8 * j) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
     }
+  }
+}
+
+// Staged variant: lane = row of a 32 x 32 block; the block is written into shared memory in the
+// swizzled layout the C tensor map expects (row pitch 128 B with SWIZZLE_128B for float, 64 B with
+// SWIZZLE_64B for half: 16-byte chunk index XOR row bits), so the quarter-warp phases of the 128-bit
+// shared stores hit distinct banks, and ONE TMA store writes the whole block as full 128-byte lines.
+template <typename TOut>
+__device__ __forceinline__ void stage_chunk(uint32_t buf, uint32_t lane, const uint32_t (&v)[32]);
+
+template <>
+__device__ __forceinline__ void stage_chunk<float>(uint32_t buf, uint32_t lane, const uint32_t (&v)[32]) {
+  const uint32_t row = buf + lane * 128u;
+#pragma unroll
+  for (uint32_t j = 0; j < 8; ++j) {
+    ptx::st_shared_v4(row + ((j ^ (lane & 7u)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+}
+
+template <>
+__device__ __forceinline__ void stage_chunk<__half>(uint32_t buf, uint32_t lane, const uint32_t (&v)[32]) {
+  uint32_t p[16];
+  pack_half(v, p);
+  const uint32_t row = buf + lane * 64u;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) {
+    ptx::st_shared_v4(row + ((j ^ ((lane >> 1) & 3u)) << 4), p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
   }
 }
 
@@ -126,42 +167,46 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
-// C[rows x cols] = A'[rows x k] * Bt[cols x k]^T ; A', Bt K-major, described by the tensor maps.
-// CG == 2 must be launched with cluster dimension (2, 1, 1).
-// BMN: the B operand is read MN-major straight from the reference's row-major B (K x M) — no
-// transposed copy.  Implemented for kind::f16 (64-element atoms); kind::tf32 needs B rounded to
-// TF32 anyway, so its prepared copy is written K-major.
-// FUSE_A (float only): the TF32 rounding of A runs INSIDE this kernel on four extra warps of every
-// CTA.  They sweep A in row order in granules of PREP_ROWS rows (all CTAs share each granule), write
-// the rounded copy that tmap_a describes, and count finished granules in `fuse.a_done`; the TMA
-// producer starts a tile only when its granule is complete.  Only the first granules are exposed
-// (the GEMM consumes 2048 rows per ~1.2 ms, the sweep rounds the whole of A in ~0.5 ms).
-struct FuseA {
-  const float4 *a_raw;    // caller's A (row-major rows x k)
-  float4 *a_prep;         // rounded copy (what tmap_a points at)
-  unsigned int *a_done;   // one counter per granule, zeroed by the launcher; complete == gridDim.x
-  uint32_t k_elems;
-  uint32_t late_warps;    // rounding warps per CTA that keep working after the first raster group (1..4)
-  uint32_t pre_done;      // leading granules already rounded by a separate launch before this kernel
+// Run-time launch parameters of the GEMM kernel (one struct so that the 16 instantiations share a
+// signature).
+struct GemmParams {
+  uint32_t rows, cols, k_bytes;
+  uint32_t num_stages;       // ring depth actually used (<= Geo::MAX_STAGES, what the smem allocation holds)
+  uint32_t raster_group;     // row tiles per rasterisation group
+  uint32_t tma_store;        // 1: staged TMA-store epilogue, 0: direct per-lane stores
+  uint32_t b_ready_target;   // see b_ready
+  uint64_t l2_policy;
+  unsigned int *tile_sync;        // soft wave-barrier counter or null
+  const unsigned int *b_ready;    // per column tile: preparation items finished, or null (B complete)
 };
-constexpr int PREP_WARPS = 4;
-constexpr int PREP_ROWS = 256;   // granule height = pair-tile height, so a CTA's 128 rows lie in one granule
 
-template <int KIND, typename TOut, int CG, bool BMN, bool FUSE_A>
-__global__ void __launch_bounds__(NUM_THREADS + (FUSE_A ? PREP_WARPS * 32 : 0), 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, TOut *__restrict__ C, uint32_t rows,
-                    uint32_t cols, uint32_t k_bytes, uint32_t num_stages, uint32_t raster_group,
-                    uint64_t l2_policy, unsigned int *tile_sync, FuseA fuse, unsigned long long *dbg) {
-  using G = Geo<CG>;
-  const int STAGES = int(num_stages);  // <= G::STAGES (what the shared-memory allocation holds)
-  extern __shared__ unsigned char smem_raw[];
+// C[rows x cols] = A'[rows x k] * B ; A' K-major.  B either MN-major straight from a row-major
+// k x cols array (BMN) or K-major from a cols x k transposed copy.  CG == 2 must be launched with
+// cluster dimension (2, 1, 1).
+template <int KIND, typename TOut, int CG, int BN, bool BMN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, TOut *__restrict__ C, const GemmParams p) {
+  using G = Geo<CG, BN>;
+  constexpr int ELEM_BYTES = (KIND == ptx::KIND_TF32) ? 4 : 2;
+  constexpr int BLOCK_K_ELEMS = BLOCK_K_BYTES / ELEM_BYTES;
+  constexpr int MN_ATOM = 128 / ELEM_BYTES;                 // columns per MN-major swizzle atom (128 B)
+  constexpr int MN_ATOM_BYTES = BLOCK_K_ELEMS * 128;        // one atom: BLOCK_K k-rows x 128 B
+  const int STAGES = int(p.num_stages);
+  const uint32_t rows = p.rows, cols = p.cols;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 128B-swizzled tiles must start on a 1024-byte boundary (same offset in both CTAs of a pair).
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a0 = smem_base;
   const uint32_t smem_b0 = smem_base + STAGES * G::A_STAGE_BYTES;
-  const uint32_t bar_base = smem_base + STAGES * G::STAGE_BYTES;
+  const uint32_t epi0 = smem_base + STAGES * G::STAGE_BYTES;
+  const uint32_t bar_base = epi0 + EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
@@ -177,23 +222,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t num_groups = gridDim.x / CG;
 
   const uint32_t tiles_r = (rows + G::TILE_ROWS - 1) / G::TILE_ROWS;
-  const uint32_t tiles_c = (cols + BLOCK_N - 1) / BLOCK_N;
+  const uint32_t tiles_c = (cols + BN - 1) / BN;
   const uint32_t num_tiles = tiles_r * tiles_c;
-  const uint32_t num_kb = (k_bytes + BLOCK_K_BYTES - 1) / BLOCK_K_BYTES;
-  constexpr int ELEM_BYTES = (KIND == ptx::KIND_TF32) ? 4 : 2;
-  constexpr int BLOCK_K_ELEMS = BLOCK_K_BYTES / ELEM_BYTES;
+  const uint32_t num_kb = (p.k_bytes + BLOCK_K_BYTES - 1) / BLOCK_K_BYTES;
 
   if (CG == 2) cluster_sync_all();  // both CTAs resident before the pair-wide TMEM allocation
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_b);
+    if (p.tma_store) ptx::prefetch_tensormap(&tmap_c);
     for (int s = 0; s < STAGES; ++s) {
       // ONE arrival: the (leader's) producer's arrive.expect_tx, which books the bytes of BOTH CTAs.
       // The peer's TMA transactions complete_tx on the leader's barrier; no peer arrival is needed
-      // (a remote mbarrier.arrive per k-block stalled the peer's producer for ~400 cycles: measured
-      // with MM_TCGEN05_DEBUG, the MMA thread waited 68 % of the time on data).  The phase cannot
-      // complete early because the expected byte count includes the peer's half, and the peer
-      // cannot run a phase ahead because its empty barrier is released by the same tcgen05.commit.
+      // (a remote mbarrier.arrive per k-block stalled the peer's producer for ~400 cycles and starved
+      // the MMA 68 % of the time).  The phase cannot complete early because the expected byte count
+      // includes the peer's half, and the peer cannot run a phase ahead because its empty barrier is
+      // released by the same tcgen05.commit.
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);  // tcgen05.commit (multicast to both CTAs when CG == 2)
     }
@@ -203,7 +247,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     ptx::fence_mbar_init();
   } else if (warp == 1) {
-    ptx::tmem_alloc<CG>(tmem_slot, TMEM_COLS);
+    ptx::tmem_alloc<CG>(tmem_slot, G::TMEM_COLS);
   }
   ptx::tcgen05_fence_before_sync();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -214,116 +258,83 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ================= TMA producer (one per CTA) =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      long long wait_empty = 0, t_begin = clock64();
       uint32_t tile_iter = 0;
-      int32_t a_ready = -1;
+      int32_t ready_panel = -1;
       for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++tile_iter) {
         // Soft wave barrier: do not start fetching tile #j before every CTA group has finished
         // fetching its tile #(j-1).  A ring deep enough to hide DRAM latency removes the L2-miss
         // back-pressure that otherwise keeps the co-running tiles in lock-step, the groups drift,
-        // and the A / B^T panels they share are re-read from DRAM (measured: 17.7 -> 32 GB at
+        // and the A / B panels they share are re-read from DRAM (measured: 17.7 -> 32 GB at
         // 16384^3).  Purely a performance hint: the wait is bounded, correctness never depends on it.
-        if (tile_sync != nullptr && tile_iter > 0) {
+        if (p.tile_sync != nullptr && tile_iter > 0) {
           const uint32_t target = min(tile_iter * num_groups, num_tiles);
           const long long t0 = clock64();
-          while (*reinterpret_cast<volatile unsigned int *>(tile_sync) < target) {
+          while (*reinterpret_cast<volatile unsigned int *>(p.tile_sync) < target) {
             if (clock64() - t0 > 100000) break;  // ~50 us: give up, stay correct
           }
         }
-        const TileCoord tc = tile_coord(t, tiles_r, tiles_c, raster_group);
+        const TileCoord tc = tile_coord(t, tiles_r, tiles_c, p.raster_group);
         const int32_t a_row = tc.r * G::TILE_ROWS + cta_rank * BLOCK_M;
-        const int32_t b_row = tc.c * BLOCK_N + cta_rank * G::LOAD_N;
-        if (FUSE_A) {
-          // rows [a_row, a_row + 128) lie in granule a_row / PREP_ROWS; granules complete in order
-          const int32_t granule = a_row / PREP_ROWS;
-          if (granule > a_ready && granule >= int32_t(fuse.pre_done)) {
-            // All CTAs of this persistent grid are resident (grid <= SMs, 1 CTA per SM), so the
-            // rounding warps of every CTA make progress while this thread spins.  The bound only
-            // turns an impossible-to-satisfy wait (e.g. a tool that serialises CTAs) into a trap.
-            const volatile unsigned int *flag = fuse.a_done + granule;
-            const long long t0 = clock64();
-            while (*flag < gridDim.x) {
-              if (clock64() - t0 > (1ll << 33)) __trap();
-            }
-            __threadfence();
-            asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes -> TMA reads
-            a_ready = granule;
+        const int32_t b_col = tc.c * BN + cta_rank * G::LOAD_N;
+        if (p.b_ready != nullptr && int32_t(tc.c) != ready_panel) {
+          // B's preparation kernel was ENQUEUED before this kernel and needs no resource this kernel
+          // holds, so it always makes progress; the bound only turns an impossible wait into a trap.
+          const unsigned int *flag = p.b_ready + tc.c;
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(flag) < p.b_ready_target) {
+            if (clock64() - t0 > (1ll << 34)) __trap();
           }
+          asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy writes -> TMA reads
+          ready_panel = int32_t(tc.c);
         }
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
-          if (dbg) {
-            const long long t0 = clock64();
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-            wait_empty += clock64() - t0;
-          } else {
-            ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-          }
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_a0 + stage * G::A_STAGE_BYTES;
+          const uint32_t sb = smem_b0 + stage * G::B_STAGE_BYTES;
+          const int32_t k0 = kb * BLOCK_K_ELEMS;
           if (CG == 1) {
             ptx::mbar_arrive_expect_tx(full_bar(stage), G::STAGE_BYTES);
-            ptx::tma_load_2d(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, full_bar(stage),
-                             kb * BLOCK_K_ELEMS, a_row, l2_policy);
+            ptx::tma_load_2d(sa, &tmap_a, full_bar(stage), k0, a_row, p.l2_policy);
             if (BMN) {
 #pragma unroll
               for (int j = 0; j < G::LOAD_N / MN_ATOM; ++j) {
-                ptx::tma_load_2d(smem_b0 + stage * G::B_STAGE_BYTES + j * MN_ATOM_BYTES, &tmap_b, full_bar(stage),
-                                 b_row + j * MN_ATOM, kb * BLOCK_K_ELEMS, l2_policy);
+                ptx::tma_load_2d(sb + j * MN_ATOM_BYTES, &tmap_b, full_bar(stage), b_col + j * MN_ATOM, k0, p.l2_policy);
               }
             } else {
-              ptx::tma_load_2d(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, full_bar(stage),
-                               kb * BLOCK_K_ELEMS, b_row, l2_policy);
+              ptx::tma_load_2d(sb, &tmap_b, full_bar(stage), k0, b_col, p.l2_policy);
             }
           } else {
             // both CTAs' bytes are accounted on the LEADER's barrier (peer bit 24 cleared)
             const uint32_t leader_bar = full_bar(stage) & 0xFEFFFFFFu;
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * G::STAGE_BYTES);
-            ptx::tma_load_2d_2sm(smem_a0 + stage * G::A_STAGE_BYTES, &tmap_a, leader_bar,
-                                 kb * BLOCK_K_ELEMS, a_row, l2_policy);
+            ptx::tma_load_2d_2sm(sa, &tmap_a, leader_bar, k0, a_row, p.l2_policy);
             if (BMN) {
 #pragma unroll
               for (int j = 0; j < G::LOAD_N / MN_ATOM; ++j) {
-                ptx::tma_load_2d_2sm(smem_b0 + stage * G::B_STAGE_BYTES + j * MN_ATOM_BYTES, &tmap_b, leader_bar,
-                                     b_row + j * MN_ATOM, kb * BLOCK_K_ELEMS, l2_policy);
+                ptx::tma_load_2d_2sm(sb + j * MN_ATOM_BYTES, &tmap_b, leader_bar, b_col + j * MN_ATOM, k0, p.l2_policy);
               }
             } else {
-              ptx::tma_load_2d_2sm(smem_b0 + stage * G::B_STAGE_BYTES, &tmap_b, leader_bar,
-                                   kb * BLOCK_K_ELEMS, b_row, l2_policy);
+              ptx::tma_load_2d_2sm(sb, &tmap_b, leader_bar, k0, b_col, p.l2_policy);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (tile_sync != nullptr && cta_rank == 0) atomicAdd(tile_sync, 1u);  // this group fetched its tile
-      }
-      if (dbg) {
-        dbg[blockIdx.x * 8 + 0] = wait_empty;
-        dbg[blockIdx.x * 8 + 1] = clock64() - t_begin;
+        if (p.tile_sync != nullptr && cta_rank == 0) atomicAdd(p.tile_sync, 1u);  // this group fetched its tile
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc(KIND, BLOCK_M * CG, BLOCK_N, BMN);
+      constexpr uint32_t idesc = ptx::make_idesc(KIND, BLOCK_M * CG, BN, BMN);
       uint32_t stage = 0, phase = 0, iter = 0;
-      long long wait_full = 0, wait_tmem = 0, t_begin = clock64();
       for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++iter) {
         const uint32_t as = iter & 1u;
         const uint32_t aphase = (iter >> 1) & 1u;
-        if (dbg) {
-          const long long t0 = clock64();
-          ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1);
-          wait_tmem += clock64() - t0;
-        } else {
-          ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1);
-        }
+        ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1);
         ptx::tcgen05_fence_after_sync();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        const uint32_t tmem_d = tmem_base + as * BN;
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
-          if (dbg) {
-            const long long t0 = clock64();
-            ptx::mbar_wait(full_bar(stage), phase);
-            wait_full += clock64() - t0;
-          } else {
-            ptx::mbar_wait(full_bar(stage), phase);
-          }
+          ptx::mbar_wait(full_bar(stage), phase);
           ptx::tcgen05_fence_after_sync();
           const uint64_t adesc = ptx::make_smem_desc_k_sw128(smem_a0 + stage * G::A_STAGE_BYTES);
           const uint64_t bdesc = BMN ? ptx::make_smem_desc_mn_sw128(smem_b0 + stage * G::B_STAGE_BYTES, MN_ATOM_BYTES)
@@ -348,69 +359,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (dbg) {
-        dbg[blockIdx.x * 8 + 2] = wait_full;
-        dbg[blockIdx.x * 8 + 3] = wait_tmem;
-        dbg[blockIdx.x * 8 + 4] = clock64() - t_begin;
-      }
-    }
-  } else if (FUSE_A && warp >= NUM_THREADS / 32) {
-    // ================= A rounding (warps 6..9 of every CTA) =================
-    const uint32_t pt = threadIdx.x - NUM_THREADS;             // 0..127 within the CTA's prep group
-    const uint32_t k4 = fuse.k_elems / 4;
-    const uint32_t granules = (rows + PREP_ROWS - 1) / PREP_ROWS;
-    // The first raster group (what the first wave of tiles needs) is rounded at full speed by all
-    // four warps; after that the GEMM consumes 2048 rows per ~1.2 ms, so only `late_warps` warps
-    // keep sweeping: less HBM / L2 pressure on the GEMM's own loads.  Streaming (evict-first)
-    // accesses keep the sweep from displacing the A / B^T panels the co-running tiles share in L2.
-    const uint32_t first_granules = RASTER_GROUP_ROWS / PREP_ROWS;
-    for (uint32_t gr = fuse.pre_done; gr < granules; ++gr) {
-      const uint32_t active = (gr < first_granules) ? uint32_t(PREP_WARPS) : fuse.late_warps;
-      const size_t begin = size_t(gr) * PREP_ROWS * k4;
-      const size_t end = size_t(min(rows, (gr + 1) * PREP_ROWS)) * k4;
-      if (pt < active * 32) {
-        const size_t stride = size_t(gridDim.x) * (active * 32);
-        size_t i = begin + size_t(blockIdx.x) * (active * 32) + pt;
-        for (; i + 7 * stride < end; i += 8 * stride) {  // 8 independent 16-byte loads in flight per thread
-          float4 v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = __ldcs(fuse.a_raw + i + u * stride);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            v[u].x = round_tf32(v[u].x); v[u].y = round_tf32(v[u].y);
-            v[u].z = round_tf32(v[u].z); v[u].w = round_tf32(v[u].w);
-            __stcs(fuse.a_prep + i + u * stride, v[u]);
-          }
-        }
-        for (; i < end; i += stride) {
-          float4 v = __ldcs(fuse.a_raw + i);
-          v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-          __stcs(fuse.a_prep + i, v);
-        }
-        __threadfence();                                        // this thread's stores visible GPU-wide
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(PREP_WARPS * 32) : "memory");  // the CTA's prep warps only
-      if (pt == 0) atomicAdd(fuse.a_done + gr, 1u);
     }
   } else {
     // ================= epilogue (warps 2..5 of every CTA) =================
     const uint32_t quarter = warp & 3u;  // TMEM lanes [32*quarter, +32) are this warp's
+    const uint32_t buf = epi0 + quarter * EPI_BUF_BYTES;
     uint32_t iter = 0;
     for (uint32_t t = group_id; t < num_tiles; t += num_groups, ++iter) {
-      const TileCoord tc = tile_coord(t, tiles_r, tiles_c, raster_group);
+      const TileCoord tc = tile_coord(t, tiles_r, tiles_c, p.raster_group);
       const uint32_t as = iter & 1u;
       const uint32_t aphase = (iter >> 1) & 1u;
       ptx::mbar_wait(tmem_full_bar(as), aphase);
       ptx::tcgen05_fence_after_sync();
-      const uint32_t row = tc.r * G::TILE_ROWS + cta_rank * BLOCK_M + quarter * 32 + lane;
-      TOut *crow = C + size_t(row) * cols;
-      const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + as * BLOCK_N;
+      const uint32_t row0 = tc.r * G::TILE_ROWS + cta_rank * BLOCK_M + quarter * 32;
+      const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + as * BN;
+      if (p.tma_store) {
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(taddr0 + chunk * 32, v);
-        ptx::tmem_ld_wait();
-        if (row < rows) store_chunk<TOut>(crow, v, tc.c * BLOCK_N + chunk * 32, cols);
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(taddr0 + chunk * 32, v);
+          ptx::tmem_ld_wait();
+          const uint32_t col = tc.c * BN + chunk * 32;
+          if (row0 < rows && col < cols) {                        // warp-uniform
+            if (lane == 0) ptx::tma_store_wait_read<0>();         // the previous block has left the buffer
+            __syncwarp();
+            stage_chunk<TOut>(buf, lane, v);
+            ptx::fence_proxy_async_smem();                        // generic-proxy smem writes -> TMA read
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tmap_c, buf, int32_t(col), int32_t(row0));  // clipped to rows x cols by the map
+              ptx::tma_store_commit();
+            }
+          }
+        }
+      } else {
+        const uint32_t row = row0 + lane;
+        TOut *crow = C + size_t(row) * cols;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(taddr0 + chunk * 32, v);
+          ptx::tmem_ld_wait();
+          if (row < rows) store_chunk<TOut>(crow, v, tc.c * BN + chunk * 32, cols);
+        }
       }
       ptx::tcgen05_fence_before_sync();
       __syncwarp();
@@ -419,13 +410,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         else ptx::mbar_arrive_cluster(tmem_empty_bar(as), 0);  // the leader's MMA issuer waits on it
       }
     }
+    if (p.tma_store && lane == 0) ptx::tma_store_wait_all<0>();  // stores complete before the CTA's smem goes away
   }
 
   ptx::tcgen05_fence_before_sync();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     ptx::tcgen05_fence_after_sync();
-    ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+    ptx::tmem_dealloc<CG>(tmem_base, G::TMEM_COLS);
   }
 }
 
@@ -442,6 +434,77 @@ round_tf32_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, size
     v.z = round_tf32(v.z);
     v.w = round_tf32(v.w);
     dst[i] = v;
+  }
+}
+
+// B (row-major K x M, 16-byte vectors) -> dst (same layout), panel by panel: a work item is
+// PANEL_ROWS k-rows of one panel of `panel_v` vectors per row; items are numbered panel-major and
+// dealt round-robin to the CTAs of a persistent grid, so panels complete in ascending order.  Each
+// finished item bumps ready[panel] (release pattern: every thread fences its stores, the CTA syncs,
+// one thread adds).  ROUND: elements are floats rounded to nearest TF32; otherwise a plain copy.
+// `parts` non-null: k-row r is read from parts[r / part_rows] — full-size K x M arrays on (peer) GPUs
+// of which only that slice of rows is valid; rows whose source IS the destination are skipped.
+constexpr int PREP_THREADS = 512;
+constexpr int PREP_WARPS = PREP_THREADS / 32;
+constexpr int PANEL_ROWS = 64;
+constexpr int PANEL_ROW_SLOTS = PANEL_ROWS / PREP_WARPS;  // rows per warp per item (4)
+
+template <bool ROUND>
+__device__ __forceinline__ uint4 prep_vec(uint4 v) {
+  if (ROUND) {
+    v.x = __float_as_uint(round_tf32(__uint_as_float(v.x)));
+    v.y = __float_as_uint(round_tf32(__uint_as_float(v.y)));
+    v.z = __float_as_uint(round_tf32(__uint_as_float(v.z)));
+    v.w = __float_as_uint(round_tf32(__uint_as_float(v.w)));
+  }
+  return v;
+}
+
+template <bool ROUND>
+__global__ void __launch_bounds__(PREP_THREADS)
+prep_b_panels_kernel(const uint4 *__restrict__ single, const uint4 *const *__restrict__ parts, uint32_t part_rows,
+                     uint4 *__restrict__ dst, uint32_t k, uint32_t row_v, uint32_t panel_v,
+                     unsigned int *__restrict__ ready) {
+  const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const uint32_t panels = (row_v + panel_v - 1) / panel_v;
+  const uint32_t items_per_panel = (k + PANEL_ROWS - 1) / PANEL_ROWS;
+  const uint32_t items = panels * items_per_panel;
+  for (uint32_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const uint32_t panel = item / items_per_panel;
+    const uint32_t r0 = (item - panel * items_per_panel) * PANEL_ROWS;
+    const uint32_t v0 = panel * panel_v;
+    const uint32_t w = min(panel_v, row_v - v0);
+    for (uint32_t c0 = 0; c0 < w; c0 += 64) {   // 64 vectors (1 KiB) of a row per pass: 8 loads in flight per thread
+      uint4 buf[PANEL_ROW_SLOTS][2];
+      bool live[PANEL_ROW_SLOTS][2];
+#pragma unroll
+      for (int u = 0; u < PANEL_ROW_SLOTS; ++u) {
+        const uint32_t r = r0 + warp + u * PREP_WARPS;
+        const uint4 *src = single;
+        if (parts != nullptr && r < k) src = parts[r / part_rows];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t c = c0 + lane + 32 * h;
+          const size_t off = size_t(r) * row_v + v0 + c;
+          live[u][h] = (r < k) && (c < w) && (src + off != static_cast<const uint4 *>(dst) + off);
+          if (live[u][h]) buf[u][h] = src[off];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PANEL_ROW_SLOTS; ++u) {
+        const uint32_t r = r0 + warp + u * PREP_WARPS;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t c = c0 + lane + 32 * h;
+          if (live[u][h]) dst[size_t(r) * row_v + v0 + c] = prep_vec<ROUND>(buf[u][h]);
+        }
+      }
+    }
+    if (ready != nullptr) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(ready + panel, 1u);
+    }
   }
 }
 
@@ -549,44 +612,47 @@ split3_transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, 
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-// K-major operand: `rows` rows of `k_elems` elements, row pitch k_elems * elem_bytes;
-// box = {128 bytes of K, box_rows}, 128-byte swizzle, out-of-bounds reads return zeros
-// (neutral for (Multiply, Add) — SURVEY.md section 5 trap 3).
-int make_operand_map(CUtensorMap *map, const void *base, int dtype, uint64_t rows, uint64_t k_elems,
-                     uint32_t box_rows) {
+CUtensorMapDataType tma_dtype(int dtype) {
+  return dtype == MM_DTYPE_FLOAT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
+int encode(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+           uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle, const char *what) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  const uint32_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
-  cuuint64_t gdim[2] = {k_elems, rows};
-  cuuint64_t gstride[1] = {k_elems * eb};
-  cuuint32_t box[2] = {uint32_t(BLOCK_K_BYTES / eb), box_rows};
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, dtype == MM_DTYPE_FLOAT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
-                   2, const_cast<void *>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, dt, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+    return fail(MM_ERR_CUDA, std::string("cuTensorMapEncodeTiled (") + what + ") failed with CUresult " +
+                                 std::to_string(int(r)));
   }
   return MM_OK;
 }
 
-// MN-major B operand read from row-major B (K x M): box = {64 elements of M (128 B), 64 k-rows}.
-int make_b_mn_map(CUtensorMap *map, const void *base, uint64_t k, uint64_t m) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[2] = {m, k};
-  cuuint64_t gstride[1] = {m * 2};
-  cuuint32_t box[2] = {uint32_t(MN_ATOM), uint32_t(BLOCK_K_BYTES / 2)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled (MN-major B) failed with CUresult " + std::to_string(int(r)));
-  }
-  return MM_OK;
+// K-major operand: `rows` rows of `k_elems` elements; box = {128 bytes of K, box_rows}, 128-byte
+// swizzle, out-of-bounds reads return zeros (neutral for (Multiply, Add) — SURVEY.md section 5 trap 3).
+int make_operand_map(CUtensorMap *map, const void *base, int dtype, uint64_t rows, uint64_t k_elems, uint32_t box_rows) {
+  const uint32_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  return encode(map, tma_dtype(dtype), base, k_elems, rows, k_elems * eb, uint32_t(BLOCK_K_BYTES / eb), box_rows,
+                CU_TENSOR_MAP_SWIZZLE_128B, "K-major operand");
+}
+
+// MN-major B operand read from row-major B (K x M): box = {one 128-byte atom of columns, BLOCK_K k-rows}.
+int make_b_mn_map(CUtensorMap *map, const void *base, int dtype, uint64_t k, uint64_t m) {
+  const uint32_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  return encode(map, tma_dtype(dtype), base, m, k, m * eb, 128 / eb, uint32_t(BLOCK_K_BYTES / eb),
+                CU_TENSOR_MAP_SWIZZLE_128B, "MN-major B");
+}
+
+// C (row-major rows x m) for the epilogue's TMA stores: 32 x 32 blocks, swizzle = row pitch of the block.
+int make_c_map(CUtensorMap *map, void *base, int dtype, uint64_t rows, uint64_t m) {
+  const uint32_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  return encode(map, tma_dtype(dtype), base, m, rows, m * eb, 32, 32,
+                eb == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "C");
 }
 
 int num_sms() {
@@ -599,68 +665,103 @@ int num_sms() {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <typename T, bool ROUND>
-void launch_transpose(const void *src, void *dst, uint32_t src_rows, uint32_t src_cols,
-                      cudaStream_t stream) {
+void launch_transpose(const void *src, void *dst, uint32_t src_rows, uint32_t src_cols, cudaStream_t stream) {
   dim3 grid((src_cols + 63) / 64, (src_rows + 63) / 64);
-  transpose_prep_kernel<T, ROUND><<<grid, 256, 0, stream>>>(static_cast<const T *>(src),
-                                                           static_cast<T *>(dst), src_rows, src_cols);
+  transpose_prep_kernel<T, ROUND><<<grid, 256, 0, stream>>>(static_cast<const T *>(src), static_cast<T *>(dst),
+                                                           src_rows, src_cols);
+}
+
+bool split3(int dtype, int flags) { return dtype == MM_DTYPE_FLOAT && (flags & MM_FLAG_TF32X3); }
+
+int launch_panels(bool round, const BSource &src, void *dst, size_t elem_bytes, unsigned k, unsigned m,
+                  unsigned panel_cols, unsigned int *ready, int grid, cudaStream_t stream) {
+  const uint32_t row_v = uint32_t(size_t(m) * elem_bytes / 16);
+  const uint32_t panel_v = uint32_t(size_t(panel_cols) * elem_bytes / 16);
+  const uint4 *single = static_cast<const uint4 *>(src.b);
+  const uint4 *const *parts = reinterpret_cast<const uint4 *const *>(src.src);
+  if (round) {
+    prep_b_panels_kernel<true><<<grid, PREP_THREADS, 0, stream>>>(single, parts, src.part_rows, static_cast<uint4 *>(dst),
+                                                                 k, row_v, panel_v, ready);
+  } else {
+    prep_b_panels_kernel<false><<<grid, PREP_THREADS, 0, stream>>>(single, parts, src.part_rows, static_cast<uint4 *>(dst),
+                                                                  k, row_v, panel_v, ready);
+  }
+  MM_CUDA_TRY(cudaGetLastError());
+  return MM_OK;
 }
 
 }  // namespace
 
-// Tail of the scratch: [granule counters of the fused A rounding, 64 KiB][soft wave-barrier counter, 256 B]
+// Tail of the scratch: [panel counters of B's preparation, 64 KiB][soft wave-barrier counter, 256 B]
 constexpr size_t TILE_SYNC_BYTES = 256;
-constexpr size_t A_DONE_BYTES = 64 * 1024;  // 16384 granules of 256 rows = 4 Mi rows
-constexpr size_t TAIL_BYTES = TILE_SYNC_BYTES + A_DONE_BYTES;
+constexpr size_t B_READY_BYTES = 64 * 1024;  // 16384 panels of >= 128 columns
+constexpr size_t TAIL_BYTES = TILE_SYNC_BYTES + B_READY_BYTES;
+static_assert(TAIL_BYTES == kTcgen05TailBytes, "common.cuh and gemm_tcgen05.cu disagree on the scratch tail");
 
-static bool split3(int dtype, int flags) { return dtype == MM_DTYPE_FLOAT && (flags & MM_FLAG_TF32X3); }
-
-// half: B is consumed MN-major straight from the caller's row-major K x M array (no B^T copy).
-// MM_TCGEN05_B_MN=0 restores the transposed-copy path for A/B measurements.
-bool tcgen05_b_direct(int dtype) {
-  static const bool enabled = [] {
-    const char *e = std::getenv("MM_TCGEN05_B_MN");
-    return !(e && e[0] == '0');
-  }();
-  return dtype == MM_DTYPE_HALF && enabled;
+Tcgen05Counters tcgen05_counters(void *scratch, size_t scratch_bytes) {
+  unsigned char *tail = static_cast<unsigned char *>(scratch) + scratch_bytes;
+  return Tcgen05Counters{reinterpret_cast<unsigned int *>(tail - TILE_SYNC_BYTES),
+                         reinterpret_cast<unsigned int *>(tail - TAIL_BYTES)};
 }
 
-size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m, int flags) {
-  if (tcgen05_b_direct(dtype)) return 0;
+bool tcgen05_b_mn(int dtype, int flags, const Tuning &t) { return t.b_mn() && !split3(dtype, flags); }
+
+bool tcgen05_b_in_place(int dtype, int flags, const Tuning &t) {
+  return tcgen05_b_mn(dtype, flags, t) && (dtype == MM_DTYPE_HALF || t.tf32_no_round());
+}
+
+size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m, int flags, const Tuning &t) {
+  if (tcgen05_b_in_place(dtype, flags, t)) return 0;
   const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
   return align_up(size_t(m) * k * eb * (split3(dtype, flags) ? 3 : 1), 1024);
 }
 
-size_t tcgen05_scratch_bytes(int dtype, unsigned n, unsigned k, unsigned m, int flags) {
+size_t tcgen05_scratch_bytes(int dtype, unsigned n, unsigned k, unsigned m, int flags, const Tuning &t) {
   const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
-  size_t bytes = TAIL_BYTES + tcgen05_bt_bytes(dtype, k, m, flags);  // counters (tail) + B^T
+  size_t bytes = TAIL_BYTES + tcgen05_bt_bytes(dtype, k, m, flags, t);  // counters (tail) + B copy
   if (dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) {
     bytes += align_up(size_t(n) * k * eb * (split3(dtype, flags) ? 3 : 1), 1024);
   }
   return bytes;
 }
 
-// Experiment hook (scripts/exp_tf32_rounding.py): feed raw fp32 bits to kind::tf32 to MEASURE the
-// truncation bias that motivates the rounding pass.  Never set in production.
-static bool experiment_no_round() {
-  static const bool v = std::getenv("MM_EXPERIMENT_TF32_NO_ROUND") != nullptr;
-  return v;
+// Copy row-sliced B (slices on peer GPUs) into one local array: the NVLink all-gather of the
+// multi-GPU path for the kernel families that consume B as stored.
+int gather_b_rows(const BSource &src, void *dst, size_t elem_bytes, unsigned k, unsigned m, cudaStream_t stream) {
+  return launch_panels(false, src, dst, elem_bytes, k, m, /*panel_cols=*/unsigned(1024 / elem_bytes), nullptr,
+                       num_sms() * 2, stream);
 }
 
-// B (row-major K x M) -> B^T (M x K, K-major MMA operand) into `bt`; float is rounded to TF32.
-int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m, int flags,
-                      const void **b_op, cudaStream_t stream) {
+int tcgen05_prepare_b(int dtype, const BSource &src, void *bt, unsigned k, unsigned m, int flags, const Tuning &t,
+                      const void **b_op, unsigned int *ready, unsigned *ready_target, cudaStream_t stream) {
   *b_op = bt;
-  if (tcgen05_b_direct(dtype)) {
-    *b_op = b;  // nothing to prepare
-    return MM_OK;
+  if (ready_target) *ready_target = 0;
+  const bool parts = src.src != nullptr;
+  const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  if (tcgen05_b_mn(dtype, flags, t)) {
+    const bool in_place = tcgen05_b_in_place(dtype, flags, t);
+    if (in_place && !parts) {
+      *b_op = src.b;  // nothing to prepare
+      return MM_OK;
+    }
+    // float: rounded copy (same layout).  half / unrounded float with slices: plain gather into `bt`.
+    const unsigned panel_cols = unsigned(t.block_n());
+    const unsigned panels = ceil_div(m, panel_cols);
+    const bool publish = ready != nullptr && panels <= B_READY_BYTES / sizeof(unsigned int);
+    if (publish && ready_target) *ready_target = ceil_div(k, PANEL_ROWS);
+    // co-resident persistent grid (one 512-thread CTA per SM next to the GEMM's CTA) when the GEMM
+    // consumes panels while this runs; a wider grid when it runs alone in stream order
+    const int grid = publish ? num_sms() : num_sms() * 2;
+    return launch_panels(!in_place, src, bt, eb, k, m, panel_cols, publish ? ready : nullptr, grid, stream);
   }
+  // K-major copy B^T (M x K): tuning knob b_mn = 0, and always for the 3xTF32 split
+  const void *b = src.b;
+  if (parts) return fail(MM_ERR_UNSUPPORTED, "row-sliced B needs the MN-major B path (gather it first)");
   if (split3(dtype, flags)) {
     dim3 grid((m + 63) / 64, (k + 63) / 64);
-    split3_transpose_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const float *>(b),
-                                                           static_cast<float *>(bt), k, m);
+    split3_transpose_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const float *>(b), static_cast<float *>(bt), k, m);
   } else if (dtype == MM_DTYPE_FLOAT) {
-    if (experiment_no_round()) {
+    if (t.tf32_no_round()) {
       launch_transpose<float, false>(b, bt, k, m, stream);
     } else {
       launch_transpose<float, true>(b, bt, k, m, stream);
@@ -673,27 +774,12 @@ int tcgen05_prepare_b(int dtype, const void *b, void *bt, unsigned k, unsigned m
 }
 
 // `rows` rows of A -> the K-major A operand.  Row-major float A is rounded into `aprep`; row-major
-// half A is used in place; A stored K x N (`transposed`, leading dimension n_total, only whole
+// half A is used in place; A stored K x N (`transposed`, leading dimension = rows, only whole
 // matrices) is transposed into `aprep`.  *a_op receives the operand pointer.
-int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, int flags,
-                      const void **a_op, const void **a_raw, cudaStream_t stream) {
+int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsigned k, int flags, const Tuning &t,
+                      const void **a_op, cudaStream_t stream) {
   const bool transposed = (flags & MM_FLAG_TRANSPOSED_A) != 0;
   *a_op = a;
-  *a_raw = nullptr;
-  if (tcgen05_fuse_a(dtype, flags) && size_t(rows) / PREP_ROWS < A_DONE_BYTES / sizeof(unsigned int)) {
-    // The GEMM kernel rounds A into `aprep` itself, in the background.  The rows of the first
-    // raster group — what the first wave of tiles needs before it can start — are rounded here by
-    // the stand-alone kernel (25 us at 16384^3), so that the GEMM does not begin with a stall.
-    const unsigned head = std::min<unsigned>(rows, RASTER_GROUP_ROWS);
-    const size_t count4 = size_t(head) * k / 4;
-    const int blocks = int(std::min<size_t>((count4 + 255) / 256, size_t(num_sms()) * 16));
-    round_tf32_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float4 *>(a), static_cast<float4 *>(aprep),
-                                                 count4);
-    MM_CUDA_TRY(cudaGetLastError());
-    *a_op = aprep;
-    *a_raw = a;
-    return MM_OK;
-  }
   if (split3(dtype, flags)) {
     if (transposed) {
       dim3 grid((rows + 63) / 64, (k + 63) / 64);
@@ -708,13 +794,13 @@ int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsi
     *a_op = aprep;
   } else if (dtype == MM_DTYPE_FLOAT) {
     if (transposed) {
-      if (experiment_no_round()) {
+      if (t.tf32_no_round()) {
         launch_transpose<float, false>(a, aprep, k, rows, stream);
       } else {
         launch_transpose<float, true>(a, aprep, k, rows, stream);  // A stored K x N -> N x K
       }
       *a_op = aprep;
-    } else if (!experiment_no_round()) {
+    } else if (!t.tf32_no_round()) {
       const size_t count4 = size_t(rows) * k / 4;
       const int blocks = int(std::min<size_t>((count4 + 255) / 256, size_t(num_sms()) * 16));
       round_tf32_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float4 *>(a),
@@ -729,29 +815,38 @@ int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsi
   return MM_OK;
 }
 
-// 1 = single-CTA tiles, 2 = cta_group::2 CTA pairs (default).  MM_TCGEN05_CTA_GROUP overrides for A/B runs.
-static int cta_group_choice() {
-  static const int v = [] {
-    const char *e = std::getenv("MM_TCGEN05_CTA_GROUP");
-    return (e && e[0] == '1') ? 1 : 2;
-  }();
-  return v;
-}
+namespace {
 
-template <int KIND, typename TOut, int CG, bool BMN, bool FUSE_A>
-static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_b, void *c, unsigned rows,
-                               unsigned m, uint32_t k_bytes, unsigned int *tile_sync, FuseA fuse,
-                               cudaStream_t stream) {
-  using G = Geo<CG>;
-  auto kern = gemm_tcgen05_kernel<KIND, TOut, CG, BMN, FUSE_A>;
-  MM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G::SMEM_BYTES)));
-  const uint32_t tiles = ceil_div(rows, G::TILE_ROWS) * ceil_div(m, BLOCK_N);
+struct LaunchPlan {
+  const CUtensorMap *map_a, *map_b, *map_c;
+  void *c;
+  GemmParams p;
+  int requested_stages;
+  bool attributes_only;  // dry run: set the function attribute (loads the kernel), launch nothing
+  cudaStream_t stream;
+};
+
+template <int KIND, typename TOut, int CG, int BN, bool BMN>
+int launch_gemm_variant(LaunchPlan plan) {
+  using G = Geo<CG, BN>;
+  auto kern = gemm_tcgen05_kernel<KIND, TOut, CG, BN, BMN>;
+  // Ring depth: the deepest that fits unless the tuning asks for less.  Measured (float 16384^3 /
+  // half 32768^3, CTA pairs, WITH the soft wave barrier): depth 4 leaves the tensor pipe 79-86 %
+  // active, depth 5-6 reach 96-98 % at unchanged DRAM traffic.
+  const int stages = plan.requested_stages <= 0 ? G::MAX_STAGES
+                                                 : std::min(std::max(plan.requested_stages, 2), int(G::MAX_STAGES));
+  const size_t smem = G::smem_bytes(stages);
+  MM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G::smem_bytes(G::MAX_STAGES))));
+  if (plan.attributes_only) return MM_OK;
+  plan.p.num_stages = uint32_t(stages);
+  plan.p.raster_group = std::max<uint32_t>(1u, plan.p.raster_group / G::TILE_ROWS);  // rows -> row tiles
+  const uint32_t tiles = ceil_div(plan.p.rows, G::TILE_ROWS) * ceil_div(plan.p.cols, BN);
   const uint32_t groups = std::min<uint32_t>(tiles, uint32_t(num_sms()) / CG);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * CG);
-  cfg.blockDim = dim3(NUM_THREADS + (FUSE_A ? PREP_WARPS * 32 : 0));
-  cfg.dynamicSmemBytes = G::SMEM_BYTES;
-  cfg.stream = stream;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = plan.stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
@@ -759,166 +854,138 @@ static int launch_gemm_variant(const CUtensorMap &map_a, const CUtensorMap &map_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // MM_TCGEN05_DEBUG=1 (diagnostics only): per-CTA stall cycle counters, printed after a sync
-  static const bool debug = std::getenv("MM_TCGEN05_DEBUG") != nullptr;
-  unsigned long long *dbg = nullptr;
-  if (debug) {
-    MM_CUDA_TRY(cudaMalloc(&dbg, sizeof(unsigned long long) * 8 * cfg.gridDim.x));
-    MM_CUDA_TRY(cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 8 * cfg.gridDim.x, stream));
-  }
-  // tuning knobs (diagnostics): ring depth and the TMA loads' L2 eviction priority
-  // Ring depth actually used (<= G::STAGES, the allocation).  Measured (profiles/r01_exp_tile_sync.log,
-  // float 16384^3 / half 32768^3, CTA pairs, WITH the soft wave barrier): depth 4 leaves the tensor
-  // pipe 79-86 % active, depth 5-6 reach 96-98 % at unchanged DRAM traffic (17.7 / 68.8 GB).  Without
-  // the barrier depth >= 5 multiplied the DRAM re-reads (27.6 / 31.7 GB at depth 5 / 6, 246 GB for
-  // half at depth 6) and lowered the sustained, power-capped rate.
-  static const uint32_t stages = [] {
-    const char *e = std::getenv("MM_TCGEN05_STAGES");
-    const int dflt = G::STAGES;
-    const int v = e ? std::atoi(e) : dflt;
-    return uint32_t(std::min(std::max(v, 2), int(G::STAGES)));
-  }();
-  static const uint64_t l2_policy = [] {
-    const char *e = std::getenv("MM_TCGEN05_L2");
-    if (e && e[0] == 'f') return ptx::L2_EVICT_FIRST;
-    if (e && e[0] == 'n') return ptx::L2_EVICT_NORMAL;
-    if (e && e[0] == 'l') return ptx::L2_EVICT_LAST;
-    return ptx::L2_EVICT_NORMAL;
-  }();
-  // rows of C per rasterisation group = the height of the patch that co-running tiles share
-  // through L2 (the "memory tile" of the reference's I/O model); scripts/tile_sweep.py sweeps it
-  static const uint32_t raster_group = [] {
-    const char *e = std::getenv("MM_TCGEN05_RASTER_ROWS");
-    const int rows_per_group = e ? std::atoi(e) : RASTER_GROUP_ROWS;
-    return uint32_t(std::max(1, rows_per_group / G::TILE_ROWS));
-  }();
-  static const bool use_tile_sync = [] {
-    const char *e = std::getenv("MM_TCGEN05_TILE_SYNC");
-    return !(e && e[0] == '0');
-  }();
-  if (!use_tile_sync) tile_sync = nullptr;
-  if (tile_sync) MM_CUDA_TRY(cudaMemsetAsync(tile_sync, 0, sizeof(unsigned int), stream));
-  if (FUSE_A) {
-    const size_t granules = (size_t(rows) + PREP_ROWS - 1) / PREP_ROWS;
-    MM_CUDA_TRY(cudaMemsetAsync(fuse.a_done, 0, granules * sizeof(unsigned int), stream));
-  }
-  MM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, static_cast<TOut *>(c), uint32_t(rows), uint32_t(m),
-                                 k_bytes, stages, raster_group, l2_policy, tile_sync, fuse, dbg));
-  if (debug) {
-    MM_CUDA_TRY(cudaStreamSynchronize(stream));
-    std::vector<unsigned long long> h(8 * cfg.gridDim.x);
-    MM_CUDA_TRY(cudaMemcpy(h.data(), dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    cudaFree(dbg);
-    double s[5] = {0, 0, 0, 0, 0};
-    int nlead = 0;
-    for (unsigned b = 0; b < cfg.gridDim.x; ++b) {
-      s[0] += double(h[b * 8 + 0]);
-      s[1] += double(h[b * 8 + 1]);
-      if (h[b * 8 + 4]) {
-        ++nlead;
-        s[2] += double(h[b * 8 + 2]);
-        s[3] += double(h[b * 8 + 3]);
-        s[4] += double(h[b * 8 + 4]);
-      }
-    }
-    fprintf(stderr, "[tcgen05 debug CG=%d rows=%u m=%u] producer: wait_empty %.1f%% of %.0f cyc | mma: wait_full %.1f%% wait_tmem %.1f%% of %.0f cyc\n",
-            CG, rows, m, 100.0 * s[0] / s[1], s[1] / cfg.gridDim.x, 100.0 * s[2] / s[4], 100.0 * s[3] / s[4], s[4] / nlead);
-  }
+  if (plan.p.tile_sync) MM_CUDA_TRY(cudaMemsetAsync(plan.p.tile_sync, 0, sizeof(unsigned int), plan.stream));
+  MM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, *plan.map_a, *plan.map_b, *plan.map_c, static_cast<TOut *>(plan.c), plan.p));
   return MM_OK;
 }
 
-// float, row-major A, single-pass TF32: A's rounding can be fused into the GEMM kernel (FuseA).
-// EXPERIMENTAL, off by default (MM_TCGEN05_FUSE_A=1 enables it): measured over three variants
-// (profiles/r01_exp_fuse_a*.log) the background sweep slows the power- and bandwidth-sharing GEMM by
-// about what the separate 0.34 ms pass costs (step 10.47-10.68 ms fused vs 10.37-10.80 ms separate),
-// so the simpler path without a cross-CTA wait stays the default.
-bool tcgen05_fuse_a(int dtype, int flags) {
-  static const bool enabled = [] {
-    const char *e = std::getenv("MM_TCGEN05_FUSE_A");
-    return e && e[0] == '1';
-  }();
-  return enabled && dtype == MM_DTYPE_FLOAT && !(flags & (MM_FLAG_TRANSPOSED_A | MM_FLAG_TF32X3)) &&
-         !experiment_no_round();
+template <int KIND, typename TOut>
+int dispatch_variant(int cg, int bn, bool bmn, const LaunchPlan &plan) {
+#define MM_VARIANT(CGV, BNV, BMNV) \
+  if (cg == CGV && bn == BNV && bmn == BMNV) return launch_gemm_variant<KIND, TOut, CGV, BNV, BMNV>(plan);
+  MM_VARIANT(2, 256, true)
+  MM_VARIANT(2, 256, false)
+  MM_VARIANT(1, 256, true)
+  MM_VARIANT(1, 256, false)
+  MM_VARIANT(2, 128, true)
+  MM_VARIANT(2, 128, false)
+  MM_VARIANT(1, 128, true)
+  MM_VARIANT(1, 128, false)
+#undef MM_VARIANT
+  return fail(MM_ERR_INVALID, "no tcgen05 kernel variant for this tuning (cta_group 1|2, block_n 128|256)");
 }
 
-// C[rows x m] = Aop[rows x k] * B on the tensor cores; `b_op` is the K-major copy B^T (m x k), or
-// the caller's row-major B (k x m) when tcgen05_b_direct(dtype).  `a_raw` non-null: a_op is the
-// (not yet written) rounded-copy buffer and the kernel rounds `a_raw` into it itself; `counters`
-// then provides the per-granule completion counters.
-int tcgen05_gemm(int dtype, const void *a_op, const void *b_op, void *c, unsigned rows, unsigned k,
-                 unsigned m, int flags, unsigned int *tile_sync, const void *a_raw, unsigned int *counters,
-                 cudaStream_t stream) {
-  const unsigned k_orig = k;
+int gemm_dispatch(int dtype, const void *a_op, const void *b_op, void *c, unsigned rows, unsigned k, unsigned m,
+                  int flags, const Tuning &t, unsigned int *tile_sync, const unsigned int *b_ready,
+                  unsigned b_ready_target, bool attributes_only, cudaStream_t stream) {
   if (split3(dtype, flags)) k *= 3;  // the operands carry [hi|hi|lo] x [hi|lo|hi] per 16-block of K
   const bool is_f32 = dtype == MM_DTYPE_FLOAT;
   const size_t eb = is_f32 ? 4 : 2;
-  const int cg = cta_group_choice();
-  const bool bmn = tcgen05_b_direct(dtype);
-  CUtensorMap map_a, map_b;
-  int rc = make_operand_map(&map_a, a_op, dtype, rows, k, BLOCK_M);
-  if (rc != MM_OK) return rc;
-  rc = bmn ? make_b_mn_map(&map_b, b_op, k, m)
-           : make_operand_map(&map_b, b_op, dtype, m, k, cg == 2 ? Geo<2>::LOAD_N : Geo<1>::LOAD_N);
-  if (rc != MM_OK) return rc;
-  const uint32_t k_bytes = uint32_t(size_t(k) * eb);
-  static const uint32_t late_warps = [] {
-    const char *e = std::getenv("MM_TCGEN05_FUSE_A_LATE_WARPS");
-    return uint32_t(std::min(std::max(e ? std::atoi(e) : 1, 1), PREP_WARPS));
-  }();
-  // leading granules covered by tcgen05_prepare_a's stand-alone pass over the first raster group
-  const unsigned head = std::min<unsigned>(rows, RASTER_GROUP_ROWS);
-  const uint32_t pre_done = (head == rows) ? (rows + PREP_ROWS - 1) / PREP_ROWS : head / PREP_ROWS;
-  FuseA fuse{static_cast<const float4 *>(a_raw), static_cast<float4 *>(const_cast<void *>(a_op)), counters, k_orig,
-             late_warps, pre_done};
-  if (is_f32 && a_raw != nullptr) {
-    return cg == 2 ? launch_gemm_variant<ptx::KIND_TF32, float, 2, false, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream)
-                   : launch_gemm_variant<ptx::KIND_TF32, float, 1, false, true>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream);
+  const int cg = t.cta_group(), bn = t.block_n();
+  const bool bmn = tcgen05_b_mn(dtype, flags, t);
+  CUtensorMap map_a, map_b, map_c;
+  std::memset(&map_c, 0, sizeof(map_c));
+  LaunchPlan plan{&map_a, &map_b, &map_c, c, {}, t.stages(), attributes_only, stream};
+  if (!attributes_only) {
+    int rc = make_operand_map(&map_a, a_op, dtype, rows, k, BLOCK_M);
+    if (rc != MM_OK) return rc;
+    rc = bmn ? make_b_mn_map(&map_b, b_op, dtype, k, m) : make_operand_map(&map_b, b_op, dtype, m, k, uint32_t(bn / cg));
+    if (rc != MM_OK) return rc;
+    if (t.tma_store()) {
+      rc = make_c_map(&map_c, c, dtype, rows, m);
+      if (rc != MM_OK) return rc;
+    }
   }
-  if (is_f32) {
-    return cg == 2 ? launch_gemm_variant<ptx::KIND_TF32, float, 2, false, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream)
-                   : launch_gemm_variant<ptx::KIND_TF32, float, 1, false, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream);
+  plan.p.rows = rows;
+  plan.p.cols = m;
+  plan.p.k_bytes = uint32_t(size_t(k) * eb);
+  plan.p.raster_group = uint32_t(std::max(1, t.raster_rows()));  // in rows here; per-variant tiles in the launcher
+  plan.p.tma_store = t.tma_store() ? 1u : 0u;
+  plan.p.b_ready_target = b_ready_target;
+  plan.p.l2_policy = t.l2_policy() == 1 ? ptx::L2_EVICT_FIRST : (t.l2_policy() == 2 ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL);
+  plan.p.tile_sync = t.tile_sync() ? tile_sync : nullptr;
+  plan.p.b_ready = b_ready;
+  return is_f32 ? dispatch_variant<ptx::KIND_TF32, float>(cg, bn, bmn, plan)
+                : dispatch_variant<ptx::KIND_F16, __half>(cg, bn, bmn, plan);
+}
+
+}  // namespace
+
+// C[rows x m] = Aop[rows x k] * B on the tensor cores; `b_op` as returned by tcgen05_prepare_b.
+int tcgen05_gemm(int dtype, const void *a_op, const void *b_op, void *c, unsigned rows, unsigned k, unsigned m,
+                 int flags, const Tuning &t, unsigned int *tile_sync, const unsigned int *b_ready,
+                 unsigned b_ready_target, cudaStream_t stream) {
+  return gemm_dispatch(dtype, a_op, b_op, c, rows, k, m, flags, t, tile_sync, b_ready, b_ready_target, false, stream);
+}
+
+int tcgen05_prepare_b_async(int dtype, const BSource &src, void *local_b, void *scratch, size_t scratch_bytes,
+                            unsigned k, unsigned m, int flags, const Tuning &t, cudaStream_t stream, cudaStream_t side,
+                            cudaEvent_t ev_fork, cudaEvent_t ev_join, PreparedB *out) {
+  *out = PreparedB{};
+  const bool in_place = tcgen05_b_in_place(dtype, flags, t);
+  const bool parts = src.src != nullptr;
+  if (parts && !tcgen05_b_mn(dtype, flags, t)) {
+    // K-major copy requested (tuning / 3xTF32): assemble the slices first, then transpose locally
+    int rc = gather_b_rows(src, local_b, dtype == MM_DTYPE_FLOAT ? 4 : 2, k, m, stream);
+    if (rc != MM_OK) return rc;
+    BSource whole;
+    whole.b = local_b;
+    return tcgen05_prepare_b(dtype, whole, scratch, k, m, flags, t, &out->b_op, nullptr, nullptr, stream);
   }
-  if (bmn) {
-    return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2, true, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream)
-                   : launch_gemm_variant<ptx::KIND_F16, __half, 1, true, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream);
-  }
-  return cg == 2 ? launch_gemm_variant<ptx::KIND_F16, __half, 2, false, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream)
-                 : launch_gemm_variant<ptx::KIND_F16, __half, 1, false, false>(map_a, map_b, c, rows, m, k_bytes, tile_sync, fuse, stream);
+  void *bt = in_place ? local_b : scratch;
+  const Tcgen05Counters cnt = tcgen05_counters(scratch, scratch_bytes);
+  const unsigned panels = ceil_div(m, unsigned(t.block_n()));
+  // the panel kernel runs (float rounding, or a gather of slices), a second stream exists, the tuning allows it
+  const bool overlap = side != nullptr && t.b_overlap() != 0 && tcgen05_b_mn(dtype, flags, t) && (!in_place || parts) &&
+                       panels <= B_READY_BYTES / sizeof(unsigned int);
+  if (!overlap) return tcgen05_prepare_b(dtype, src, bt, k, m, flags, t, &out->b_op, nullptr, nullptr, stream);
+  MM_CUDA_TRY(cudaMemsetAsync(cnt.b_ready, 0, panels * sizeof(unsigned int), stream));
+  MM_CUDA_TRY(cudaEventRecord(ev_fork, stream));
+  MM_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
+  const int rc = tcgen05_prepare_b(dtype, src, bt, k, m, flags, t, &out->b_op, cnt.b_ready, &out->ready_target, side);
+  cudaEventRecord(ev_join, side);  // the side stream rejoins whatever happened above
+  out->forked = true;
+  out->ready = cnt.b_ready;
+  return rc;
 }
 
 int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_bytes) {
   if (dtype != MM_DTYPE_FLOAT && dtype != MM_DTYPE_HALF) {
     return fail(MM_ERR_UNSUPPORTED, "tcgen05 path handles float and half only");
   }
-  if (scratch_bytes < tcgen05_scratch_bytes(dtype, g.n, g.k, g.m, g.flags)) {
-    return fail(MM_ERR_INVALID, "tcgen05 scratch too small");
-  }
+  if (g.tuning == nullptr) return fail(MM_ERR_INVALID, "tcgen05 launch without tuning");
+  const Tuning &t = *g.tuning;
   if (g.dry_run) {
-    // force the lazily loaded kernels in (prep + GEMM variants) and the driver entry point
+    // force the lazily loaded kernels in (prep + the GEMM variant this tuning selects) and the driver entry point
     cudaFuncAttributes attr;
     MM_CUDA_TRY(cudaFuncGetAttributes(&attr, round_tf32_kernel));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, prep_b_panels_kernel<true>));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, prep_b_panels_kernel<false>));
     MM_CUDA_TRY(cudaFuncGetAttributes(&attr, transpose_prep_kernel<float, true>));
     MM_CUDA_TRY(cudaFuncGetAttributes(&attr, transpose_prep_kernel<__half, false>));
-    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_TF32, float, 2, false, true>));
-    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_TF32, float, 2, false, false>));
-    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, gemm_tcgen05_kernel<ptx::KIND_F16, __half, 2, true, false>));
     if (!get_encode_fn()) return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    return MM_OK;
+    return gemm_dispatch(dtype, nullptr, nullptr, nullptr, g.n, g.k, g.m, g.flags, t, nullptr, nullptr, 0, true, g.stream);
+  }
+  if (scratch_bytes < tcgen05_scratch_bytes(dtype, g.n, g.k, g.m, g.flags, t)) {
+    return fail(MM_ERR_INVALID, "tcgen05 scratch too small");
   }
   unsigned char *sp = static_cast<unsigned char *>(scratch);
-  void *bt = sp;
-  void *aprep = sp + tcgen05_bt_bytes(dtype, g.k, g.m, g.flags);
-  unsigned int *tile_sync = reinterpret_cast<unsigned int *>(sp + scratch_bytes - TILE_SYNC_BYTES);
-  unsigned int *a_done = reinterpret_cast<unsigned int *>(sp + scratch_bytes - TAIL_BYTES);
-
-  const void *b_op = nullptr;
-  int rc = tcgen05_prepare_b(dtype, g.b, bt, g.k, g.m, g.flags, &b_op, g.stream);
-  if (rc != MM_OK) return rc;
-  const void *a_op = nullptr, *a_raw = nullptr;
-  rc = tcgen05_prepare_a(dtype, g.a, aprep, g.n, g.k, g.flags, &a_op, &a_raw, g.stream);
-  if (rc != MM_OK) return rc;
-  if (g.ev_prep_done) MM_CUDA_TRY(cudaEventRecord(g.ev_prep_done, g.stream));
-  return tcgen05_gemm(dtype, a_op, b_op, g.c, g.n, g.k, g.m, g.flags, tile_sync, a_raw, a_done, g.stream);
+  void *aprep = sp + tcgen05_bt_bytes(dtype, g.k, g.m, g.flags, t);
+  const Tcgen05Counters cnt = tcgen05_counters(scratch, scratch_bytes);
+  BSource src;
+  src.b = g.b;
+  PreparedB pb;
+  const void *a_op = nullptr;
+  int rc = tcgen05_prepare_b_async(dtype, src, nullptr, scratch, scratch_bytes, g.k, g.m, g.flags, t, g.stream,
+                                   g.side_stream, g.ev_fork, g.ev_join, &pb);
+  if (rc == MM_OK) rc = tcgen05_prepare_a(dtype, g.a, aprep, g.n, g.k, g.flags, t, &a_op, g.stream);
+  if (rc == MM_OK && g.ev_prep_done) cudaEventRecord(g.ev_prep_done, g.stream);
+  if (rc == MM_OK) {
+    rc = tcgen05_gemm(dtype, a_op, pb.b_op, g.c, g.n, g.k, g.m, g.flags, t, cnt.tile_sync, pb.ready, pb.ready_target,
+                      g.stream);
+  }
+  if (pb.forked) cudaStreamWaitEvent(g.stream, g.ev_join, 0);  // join, on the error paths too
+  return rc;
 }
 
 }  // namespace mm

@@ -60,7 +60,7 @@ struct Prim<__half> {
   static __device__ __forceinline__ __half add(__half a, __half b) { return __hadd_rn(a, b); }
   static __device__ __forceinline__ __half mul(__half a, __half b) { return __hmul_rn(a, b); }
   static __device__ __forceinline__ bool lt(__half a, __half b) { return __hlt(a, b); }
-  static __device__ __forceinline__ bool nz(__half a) { return __hne(a, __ushort_as_half(0)); }
+  static __device__ __forceinline__ bool nz(__half a) { return __hneu(a, __ushort_as_half(0)); }  // `a != 0`: true for NaN
   static __device__ __forceinline__ __half zero() { return __ushort_as_half(0x0000); }
   static __device__ __forceinline__ __half one() { return __ushort_as_half(0x3C00); }
   static __device__ __forceinline__ __half max_value() { return __ushort_as_half(0x7BFF); }  // 65504

@@ -102,4 +102,26 @@ class Context {  // hlslib::ocl::Context, common/OpenCL.h:366-500
   mm_context *ctx_ = nullptr;
 };
 
+// The same lifecycle over G GPUs (mm_multi_*): C row-blocks, B uploaded in slices and assembled over NVLink.
+class MultiContext {
+ public:
+  explicit MultiContext(int gpus) { Check(mm_multi_create(gpus, nullptr, &multi_)); }
+  ~MultiContext() { mm_multi_destroy(multi_); }
+  MultiContext(MultiContext const &) = delete;
+  MultiContext &operator=(MultiContext const &) = delete;
+  void Upload(int dtype, int flags, void const *a, void const *b, unsigned n, unsigned k, unsigned m) {
+    Check(mm_multi_upload(multi_, dtype, flags, a, b, n, k, m));
+  }
+  std::pair<double, double> Execute(int dtype, int map_op, int reduce_op, int flags, unsigned n, unsigned k,
+                                    unsigned m) {
+    double dev = 0, wall = 0;
+    Check(mm_multi_execute(multi_, dtype, map_op, reduce_op, flags, n, k, m, &dev, &wall));
+    return {dev, wall};
+  }
+  void Download(int dtype, void *c, unsigned n, unsigned m) { Check(mm_multi_download(multi_, dtype, c, n, m)); }
+
+ private:
+  mm_multi *multi_ = nullptr;
+};
+
 }  // namespace mm

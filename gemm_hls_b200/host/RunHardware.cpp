@@ -4,19 +4,18 @@
 // exit codes.  Device work goes through Device.h (Context / Buffer / Kernel over the C-ABI).
 //   hw      the B200 selected by $MM_DEVICE (default 0)
 //   hw_emu  accepted for compatibility; there is no emulation target, it runs on the B200 as well
-//   MM_NUM_GPUS=G (> 1, build with NCCL)  row-block split over G GPUs, B broadcast once (MultiGpu.h)
+//   MM_NUM_GPUS=G (> 1)  C row-blocks over G GPUs inside libmm_b200.so (mm_multi_*): every GPU uploads 1/G of
+//                        B, the slices are gathered GPU-to-GPU over NVLink once, no per-step collective
 //   MM_POWER_METER=1  NVML power sampling every 10 ms while the kernel is repeated for >= 2 s, then
 //                     the reference's "Measured an average power of ... W" line (host/RunHardware.cpp:182-185)
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "Device.h"
 #include "HostProblem.h"
 #include "PowerMeter.h"
-#ifdef MM_HAS_NCCL
-#include "MultiGpu.h"
-#endif
 
 namespace {
 
@@ -108,29 +107,34 @@ void RunSingle(mmhost::Problem &problem, bool verify) {
   }
 }
 
-#ifdef MM_HAS_NCCL
-// G GPUs: C row-blocks, B broadcast once over NCCL; the reported time is the
-// slowest GPU's kernel time.
+// G GPUs: the same sequence through Device.h's MultiContext (mm_multi_upload / _execute / _download).  The
+// reported time is the slowest GPU's kernel time of the SECOND execution: the first one (untimed) loads the
+// kernels and sizes the scratch on every device, which the single-GPU ExecuteTask does in its dry run.
 void RunMulti(mmhost::Problem &problem, bool verify, int gpus) {
   auto const &shape = problem.shape();
-  std::cout << "Initializing " << gpus << " CUDA contexts and NCCL...\n" << std::flush;
-  mm::MultiGpuRun run(gpus, kDataTypeCode, kMapOpCode, kReduceOpCode, kKernelFlags, shape.n, shape.k, shape.m,
-                      sizeof(Data_t));
-  if (verify) {
-    std::cout << "Copying memory to device...\n" << std::flush;
-    run.CopyFromHost(problem.A(), problem.B());
+  std::cout << "Initializing " << gpus << " CUDA contexts...\n" << std::flush;
+  mm::MultiContext context(gpus);
+  std::cout << "Initializing device memory...\n" << std::flush;
+  std::vector<Data_t> scratch_a, scratch_b;
+  Data_t const *a = problem.A(), *b = problem.B();
+  if (!verify) {  // verify off: the reference leaves the buffers uninitialised (:99-111); any bytes will do
+    scratch_a.resize(shape.CountA());
+    scratch_b.resize(shape.CountB());
+    a = scratch_a.data();
+    b = scratch_b.data();
   }
-  std::cout << "Broadcasting B over NCCL...\n" << std::flush;
-  const double broadcast_seconds = run.BroadcastB();
+  std::cout << "Copying memory to device...\n" << std::flush;
+  context.Upload(kDataTypeCode, kKernelFlags, a, b, shape.n, shape.k, shape.m);
+  std::cout << "Creating kernel...\n" << std::flush;
+  context.Execute(kDataTypeCode, kMapOpCode, kReduceOpCode, kKernelFlags, shape.n, shape.k, shape.m);  // warm-up
   std::cout << "Executing kernel...\n" << std::flush;
-  ReportPerformance(shape, run.Execute().first);
-  std::cout << "NCCL broadcast of B took " << broadcast_seconds << " seconds on " << gpus << " GPUs.\n";
+  ReportPerformance(shape, context.Execute(kDataTypeCode, kMapOpCode, kReduceOpCode, kKernelFlags, shape.n, shape.k,
+                                           shape.m).first);
   if (verify) {
     std::cout << "Copying back result...\n" << std::flush;
-    run.CopyToHost(problem.Result());
+    context.Download(kDataTypeCode, problem.Result(), shape.n, shape.m);
   }
 }
-#endif
 
 }  // namespace
 
@@ -150,11 +154,7 @@ int main(int argc, char **argv) {
   try {
     const int gpus = EnvironmentInt("MM_NUM_GPUS", 1);
     if (gpus > 1) {
-#ifdef MM_HAS_NCCL
       RunMulti(problem, options.verify, gpus);
-#else
-      throw std::runtime_error("MM_NUM_GPUS > 1 needs a build with NCCL (MM_HAS_NCCL)");
-#endif
     } else {
       RunSingle(problem, options.verify);
     }

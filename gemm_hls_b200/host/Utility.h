@@ -52,24 +52,29 @@ template <typename T> struct Select<T, MM_OP_AND> { using type = And<T>; };
 
 }  // namespace host_op
 
-using OperatorMap = host_op::Select<Data_t, kMapOpCode>::type;
-using OperatorReduce = host_op::Select<Data_t, kReduceOpCode>::type;
+// half on the tensor cores (MM_HALF_TENSOR) accumulates in FP32 and rounds once: the host reference
+// does the same; every other configuration computes in Data_t like the reference's Naive<>.
+constexpr bool kHalfOnTensorCores = kDataIsHalf && !(kKernelFlags & MM_FLAG_EXACT) &&
+                                    kMapOpCode == MM_OP_MULTIPLY && kReduceOpCode == MM_OP_ADD;
+using Acc_t = std::conditional<kHalfOnTensorCores, float, Data_t>::type;
+using OperatorMap = host_op::Select<Acc_t, kMapOpCode>::type;
+using OperatorReduce = host_op::Select<Acc_t, kReduceOpCode>::type;
 
 // include/Utility.h:105-111 (-> CallBLAS fallback :66-74 -> Naive :18-42)
 inline void ReferenceImplementation(Data_t const *a, Data_t const *b, Data_t *c, const unsigned size_n,
                                     const unsigned size_k, const unsigned size_m) {
   for (unsigned n = 0; n < size_n; ++n) {
     for (unsigned m = 0; m < size_m; ++m) {
-      Data_t acc = OperatorReduce::identity();
+      Acc_t acc = OperatorReduce::identity();
       for (unsigned k = 0; k < size_k; ++k) {
 #ifndef MM_TRANSPOSED_A
         const Data_t elem_a = a[static_cast<size_t>(n) * size_k + k];
 #else
         const Data_t elem_a = a[static_cast<size_t>(k) * size_n + n];
 #endif
-        acc = OperatorReduce::Apply(acc, OperatorMap::Apply(elem_a, b[static_cast<size_t>(k) * size_m + m]));
+        acc = OperatorReduce::Apply(acc, OperatorMap::Apply(Acc_t(elem_a), Acc_t(b[static_cast<size_t>(k) * size_m + m])));
       }
-      c[static_cast<size_t>(n) * size_m + m] = acc;
+      c[static_cast<size_t>(n) * size_m + m] = Data_t(acc);
     }
   }
 }
@@ -95,8 +100,12 @@ inline bool VerifyAgainstReference(std::vector<Data_t> const &test, std::vector<
       bool mismatch;
       if (std::is_integral<Data_t>::value) {
         mismatch = testVal != refVal;
+      } else if (kDataIsHalf && !kHalfOnTensorCores) {
+        // the reference's branch for half: std::is_floating_point<half> is false, so it compares
+        // EXACTLY (test/TestSimulation.cpp:79-85) — the bit-exact datapath is held to that
+        mismatch = !(static_cast<float>(testVal) == static_cast<float>(refVal));
       } else {
-        // relative 1e-3, evaluated in double so that `half` takes the same branch
+        // relative 1e-3 (the reference's floating-point branch), evaluated in double
         const double t = static_cast<double>(static_cast<float>(testVal));
         const double r = static_cast<double>(static_cast<float>(refVal));
         const double td = std::is_same<Data_t, double>::value ? static_cast<double>(testVal) : t;

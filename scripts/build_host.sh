@@ -4,8 +4,8 @@
 #   usage: bash scripts/build_host.sh [outdir] [float|double|half|int|...] [Multiply|Add|...] [Add|Min|...]
 #   MM_STATIC_SIZES="N K M" in the environment builds the MM_DYNAMIC_SIZES=OFF flavour (sizes fixed at
 #   compile time, executables take no N K M arguments), as the reference's CMake option does.
-# RunHardware gets the NCCL multi-GPU driver (MM_NUM_GPUS) when the system nccl.h / libnccl are present
-# (MM_HOST_NO_NCCL=1 builds the plain single-GPU program).
+#   MM_HOST_EXACT=1 / MM_HOST_HALF_TENSOR=1 = the CMake options -DMM_EXACT=ON / -DMM_HALF_TENSOR=ON.
+# MM_NUM_GPUS=G at run time splits the call over G GPUs inside libmm_b200.so (no NCCL needed).
 set -e
 R=${GRAFT_REPO_ROOT:-$(cd "$(dirname "$0")/.." && pwd)}
 OUT=${1:-/tmp/hostbuild}; TYPE=${2:-float}; MAP=${3:-Multiply}; RED=${4:-Add}
@@ -25,7 +25,11 @@ cfg = dict(MM_HOST_DATA_TYPE=typ, MM_DATA_TYPE=typ, MM_DTYPE_CODE="MM_DTYPE_" + 
 t = open(root + "/gemm_hls_b200/host/Config.h.in").read()
 missing = set(re.findall(r"\$\{(\w+)\}", t)) - set(cfg)
 assert not missing, "Config.h.in variables without a value: %s" % sorted(missing)
-t = re.sub(r"\$\{(\w+)\}", lambda m: str(cfg[m.group(1)]), t).replace("#cmakedefine MM_EXACT", "/* #undef MM_EXACT */")
+import os
+t = re.sub(r"\$\{(\w+)\}", lambda m: str(cfg[m.group(1)]), t)
+for opt in ("MM_EXACT", "MM_HALF_TENSOR"):   # MM_HOST_EXACT=1 / MM_HOST_HALF_TENSOR=1 = the CMake options -DMM_EXACT=ON / -DMM_HALF_TENSOR=ON
+    on = os.environ.get(opt.replace("MM_", "MM_HOST_"), "") not in ("", "0")
+    t = t.replace("#cmakedefine " + opt, ("#define " + opt) if on else ("/* #undef %s */" % opt))
 open(out + "/Config.h", "w").write(t)
 PY
 cd "$OUT"
@@ -33,10 +37,5 @@ DYN="-DMM_DYNAMIC_SIZES"; [ -n "$MM_STATIC_SIZES" ] && DYN=""
 COMMON="-std=c++17 -O2 $DYN -I. -I$R/include -I$R/gemm_hls_b200/host -L$R/gemm_hls_b200 -lmm_b200 -Wl,-rpath,$R/gemm_hls_b200 -ldl -lpthread"
 g++ $R/gemm_hls_b200/host/TestSimulation.cpp $R/gemm_hls_b200/host/KernelEntry.cpp $COMMON -o TestSimulation
 g++ $R/gemm_hls_b200/host/PrintSpecifications.cpp $COMMON -o PrintSpecifications
-if [ -z "$MM_HOST_NO_NCCL" ] && [ -f /usr/include/nccl.h ] && [ -f /usr/local/cuda/include/cuda_runtime.h ]; then
-  g++ $R/gemm_hls_b200/host/RunHardware.cpp -DMM_HAS_NCCL -I/usr/local/cuda/include $COMMON -L/usr/local/cuda/lib64 -lcudart -lnccl -o RunHardware \
-    || g++ $R/gemm_hls_b200/host/RunHardware.cpp $COMMON -o RunHardware
-else
-  g++ $R/gemm_hls_b200/host/RunHardware.cpp $COMMON -o RunHardware
-fi
+g++ $R/gemm_hls_b200/host/RunHardware.cpp $COMMON -o RunHardware
 echo "host executables in $OUT: $(ls "$OUT" | tr '\n' ' ')"

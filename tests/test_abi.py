@@ -43,11 +43,12 @@ def test_library_contains_blackwell_sass(mm):
     assert "sm_100a" in sass
     assert re.search(r"UTC[A-Z]*MMA", sass), "no tcgen05.mma in SASS"
     assert "LDTM" in sass and "UTMALDG" in sass
+    assert "UTMASTG" in sass, "the epilogue's TMA stores are missing"
     assert "DMMA" in sass
 
 
 def test_static_queries(mm):
-    assert mm.lib().mm_version() >= 100
+    assert mm.lib().mm_version() >= 200
     assert [mm.lib().mm_dtype_size(d) for d in range(6)] == [2, 4, 8, 4, 4, 1]
     assert mm.memory_width(mm.FLOAT) == 16 and mm.memory_width(mm.HALF) == 32
     assert mm.memory_width(mm.DOUBLE) == 8 and mm.memory_width(mm.UINT8) == 64
@@ -57,9 +58,9 @@ def test_static_queries(mm):
     assert mm.kernel_path(mm.FLOAT, mm.ADD, mm.MIN) == "semiring_simt"
     assert mm.kernel_path(mm.FLOAT, flags=mm.FLAG_EXACT) == "semiring_simt"
     assert mm.kernel_path(mm.INT32) == "semiring_simt"
-    # float: B^T preparation + GEMM (A's TF32 rounding is fused into the GEMM kernel), 3 with MM_TCGEN05_FUSE_A=0
-    assert mm.launch_count(mm.FLOAT) in (2, 3) and mm.launch_count(mm.DOUBLE) == 1
-    assert mm.launch_count(mm.HALF) in (1, 2)
+    # float: B rounding + A rounding + GEMM; half reads both operands in place
+    assert mm.launch_count(mm.FLOAT) == 3 and mm.launch_count(mm.DOUBLE) == 1
+    assert mm.launch_count(mm.HALF) == 1
 
 
 def _has_gpu():

@@ -10,6 +10,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
 
 def _bench(*args, env=None):
@@ -33,9 +34,14 @@ def test_reference_arm_line(oracle):
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
     assert "Naive<>" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    # value = sampled operations / time: rows_per_step x K x M x 2 per step
+    # value = sampled operations / time: rows x K x sampled columns x 2 per step; the sample is FIXED
+    # (one row per physical core, first SAMPLE_COLS columns), never shrunk adaptively
+    import bench
     rows = int(cb["sample"].split()[0])
-    assert d["value"] == pytest.approx(1e-9 * 2.0 * rows * 4096 * 4096 / (1e-3 * d["ms_per_step"]), rel=1e-6)
+    assert rows == cb["cores"] == bench.host_threads()
+    assert d["value"] == pytest.approx(1e-9 * 2.0 * rows * 4096 * bench.SAMPLE_COLS / (1e-3 * d["ms_per_step"]), rel=1e-6)
+    # both arms print the same `config` (nothing run-dependent in it): the driver's same_config check
+    assert set(d["config"]) == {"workload", "baseline_config", "partition", "l2"}
 
 
 def test_reference_arm_runs_on_rank_zero_only(oracle):
@@ -70,8 +76,8 @@ def test_cpu_baseline_object_of_the_b200_arm(oracle):
 
     cb = bench.cpu_baseline_line("float", "Multiply", "Add", "GFLOP/s", k, m, a_rows_of, b)
     threads = bench.host_threads()
-    assert asked == [2 * threads]                     # small problem: two rows per thread
-    rows = min(2 * threads, 64)
+    assert asked == [threads]                         # one row per physical core, as in the reference arm
+    rows = min(threads, 64)
     assert cb["cores"] == min(threads, rows) and cb["kind"] in ("reference", "port") and cb["unit"] == "GFLOP/s"
-    assert cb["value"] == pytest.approx(1e-9 * 2.0 * rows * k * m / cb["seconds"], rel=1e-9)
-    assert cb["sample"].startswith("first %d rows of C" % rows)
+    assert cb["value"] == pytest.approx(1e-9 * 2.0 * rows * k * min(m, bench.SAMPLE_COLS) / cb["seconds"], rel=1e-9)
+    assert cb["sample"].startswith("%d rows x first %d columns of C" % (rows, min(m, bench.SAMPLE_COLS)))
