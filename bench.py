@@ -237,6 +237,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="MM_FLAG_* bits (debugging)")
     ap.add_argument("--tune", default="", help="comma-separated knob=value pairs for mm_context_set_tuning (sweeps)")
+    ap.add_argument("--emulate-ranks", type=int, default=0,
+                    help="experiments only: time ONE rank's row-block of an R-GPU split on this GPU (N/R rows); "
+                         "the printed value is that block's own rate, not a multi-GPU figure")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -244,12 +247,20 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dtype_name, mp_name, rd_name, N, K, M, cfg_label = WORKLOADS[args.workload]
+    if args.emulate_ranks > 1:
+        N = (N + args.emulate_ranks - 1) // args.emulate_ranks
+        cfg_label += " — ONE row-block of a %d-GPU split, emulated on one GPU (experiment)" % args.emulate_ranks
+        args.no_e2e = args.no_cpu = True
     ops_total = 2.0 * N * K * M
     metric = "GFLOP/s" if (mp_name, rd_name) == ("Multiply", "Add") else "GOp/s"
     metric_name = "%s at N=%d K=%d M=%d %s (%s,%s)" % (metric, N, K, M, dtype_name, mp_name, rd_name)
     # `config` names the workload and nothing run-dependent: both arms print it byte for byte
+    from gemm_hls_b200 import multi as partition   # pure-Python host logic (no CUDA needed to import)
+    grid_r, grid_c = partition.rank_grid(args.gpus, N, K, M)
     config = {"workload": "%s %dx%dx%d (%s,%s)" % (dtype_name, N, K, M, mp_name, rd_name), "baseline_config": cfg_label,
-              "partition": "C row-blocks over %d GPU(s), B replicated" % args.gpus,
+              "partition": ("C blocks over a %d x %d grid of %d GPU(s): %d row-block(s) x %d column-block(s); a rank holds (and "
+                            "prepares, every step) its A row-block and its B column-block; no collective inside a step"
+                            % (grid_r, grid_c, args.gpus, grid_r, grid_c)),
               "l2": "inputs (A+B+C = %.2f GB) far larger than the 126 MB L2; no explicit flush" %
                     (1e-9 * {"float": 4, "half": 2, "double": 8}[dtype_name] * (N * K + K * M + N * M))}
 
@@ -306,10 +317,13 @@ def main():
     es = torch.empty((), dtype=t_dt).element_size()
     tune = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.tune.split(",") if kv}
 
-    # row-block of this rank: ceil(N / world) rows, last block may be short
-    rows_per = (N + world - 1) // world
-    r0, r1 = min(N, rank * rows_per), min(N, (rank + 1) * rows_per)
-    n_local = r1 - r0
+    # Block of this rank.  Outer tiles (n0, m0) of C are fully independent (kernel/Compute.cpp:53-56), so C is cut
+    # over a grid_r x grid_c grid of ranks: rank (i, j) computes rows block i x columns block j from A's row-block i and
+    # B's column-block j.  grid_c = 1 is SURVEY.md 8e's row-block split with B replicated; a 2-D grid replicates less
+    # operand preparation per step (each rank rounds 1/grid_r of A and 1/grid_c of B instead of all of B).
+    w = {"float": 16, "half": 32, "double": 8}[dtype_name]           # columns stay multiples of the 64-byte memory word
+    r0, r1, c0, c1 = partition.rank_block(rank, (grid_r, grid_c), N, M, w)
+    n_local, m_local = r1 - r0, c1 - c0
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(5 + rank)
@@ -323,7 +337,7 @@ def main():
         b_full = torch.empty((K, M), device=dev, dtype=t_dt)
     extra = {}
     if world > 1:
-        dist.broadcast(b_full, src=0)  # the ONE collective of the path: B over NVLink/NVSwitch
+        partition.broadcast_b(b_full, 0)  # the ONE collective of the path: B over NVLink/NVSwitch
         # reported beside the step time: the same broadcast once more, now that the
         # communicator exists, timed on the device, max over ranks
         torch.cuda.synchronize()
@@ -337,7 +351,10 @@ def main():
         dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         extra["broadcast_b"] = {"ms": round(float(tb.item()), 4), "bytes": b_full.numel() * b_full.element_size(),
                                 "note": "one NCCL broadcast of B before the timed region (SURVEY.md 8e)"}
-    c_blk = torch.empty((n_local, M), device=dev, dtype=t_dt)
+    # the kernels take dense matrices (no leading dimension, like the reference): this rank's column-block of B
+    # becomes its own contiguous K x m_local array, once, with the broadcast, before the timed region
+    b_use = partition.local_b(b_full, c0, c1)
+    c_blk = torch.empty((n_local, m_local), device=dev, dtype=t_dt)
     torch.cuda.synchronize()
 
     ctx = G.Context(local_rank)
@@ -352,7 +369,7 @@ def main():
     flags = args.flags
 
     def step():
-        ctx.enqueue(dtype, mp, rd, a_blk.data_ptr(), b_full.data_ptr(), c_blk.data_ptr(), n_local, K, M,
+        ctx.enqueue(dtype, mp, rd, a_blk.data_ptr(), b_use.data_ptr(), c_blk.data_ptr(), n_local, K, m_local,
                     flags=flags, stream=stream)
 
     def barrier():
@@ -391,8 +408,8 @@ def main():
     value = 1e-9 * ops_total / (1e-3 * ms_per_step)  # whole job: all ranks' row-blocks
 
     # ---- light on-device sanity so that a wrong kernel cannot post a number (not the parity test)
-    def check_rows(got_rows, a_rows_t, what):
-        ref = a_rows_t.double() @ b_full.double()
+    def check_rows(got_rows, a_rows_t, what, b_t=None):
+        ref = a_rows_t.double() @ (b_full if b_t is None else b_t).double()
         rel = ((got_rows.double() - ref).abs() / ref.abs().clamp_min(1e-30)).max().item()
         tol = 1e-2 if dtype_name == "half" else 1e-3
         if not (rel <= tol):
@@ -402,14 +419,14 @@ def main():
     if (mp_name, rd_name) == ("Multiply", "Add"):
         rows = torch.tensor([0, n_local // 2, n_local - 1], device=dev)
         extra["check"] = "3 rows of C vs fp64 torch.matmul on device: max rel err %.2e" % check_rows(c_blk[rows], a_blk[rows],
-                                                                                                 "device-timed")
+                                                                                                 "device-timed", b_use)
 
     out = None
     if rank == 0:
         peaks = load_peaks()
         path = G.kernel_path(dtype, mp, rd, flags)
         main_avg_s = main_s / max(calls, 1)
-        local_ops = 2.0 * n_local * K * M
+        local_ops = 2.0 * n_local * K * m_local
         if path in ("tcgen05_tf32", "tcgen05_f16"):
             # burst figure when the whole timed region is shorter than the ~1 s it takes the power
             # cap to pull the clocks down, the sustained one for a seconds-long back-to-back loop
@@ -439,7 +456,7 @@ def main():
         roof["peak_source"] = peak_note
         # DRAM bytes of the dominant kernel: only a figure MEASURED for exactly this workload, GPU count and
         # default tuning (one `ncu --set full` capture per round, profiles/ncu_traffic.json); null otherwise
-        roof["algorithmic_bytes"] = es * (n_local * K + K * M + n_local * M)
+        roof["algorithmic_bytes"] = es * (n_local * K + K * m_local + n_local * m_local)
         traffic = None
         tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tr_path) and not tune and flags == 0:

@@ -36,7 +36,7 @@ struct KnobInfo {
 const KnobInfo kKnobs[MM_TUNE_COUNT] = {
     {"MM_TCGEN05_CTA_GROUP", 2}, {"MM_TCGEN05_BLOCK_N", 256},  {"MM_TCGEN05_STAGES", 0},
     {"MM_TCGEN05_RASTER_ROWS", 2048}, {"MM_TCGEN05_TILE_SYNC", 1}, {"MM_TCGEN05_B_MN", 1},
-    {"MM_TCGEN05_L2", 0}, {"MM_TCGEN05_B_OVERLAP", 1}, {"MM_TCGEN05_TMA_STORE", 1},
+    {"MM_TCGEN05_L2", 0}, {"MM_TCGEN05_B_OVERLAP", 0}, {"MM_TCGEN05_TMA_STORE", 1},
     {"MM_DMMA_TILE_ROWS", 0}, {"MM_EXPERIMENT_TF32_NO_ROUND", 0},
 };
 
@@ -368,7 +368,7 @@ struct Pipeline {
     MM_CUDA_TRY(cudaEventRecord(ctx->ev_start, ctx->stream));
     mm::BSource src;
     src.b = db;
-    if (bp.parts > 1) {
+    if (bp.parts_dev != nullptr) {  // also with a single slice: the GPUs that did not upload it read it from its owner
       src.src = bp.parts_dev;
       src.parts = bp.parts;
       src.part_rows = bp.part_rows;
@@ -381,7 +381,7 @@ struct Pipeline {
                                        ctx->side, ctx->ev_fork, ctx->ev_join, &pb);
       if (rc != MM_OK) return rc;
       aprep = static_cast<unsigned char *>(ctx->scratch.ptr) + mm::tcgen05_bt_bytes(dtype, k, m, flags, t);
-    } else if (bp.parts > 1) {
+    } else if (bp.parts_dev != nullptr) {
       rc = mm::gather_b_rows(src, db, es, k, m, ctx->stream);  // the peers' slices into this GPU's B, over NVLink
       if (rc != MM_OK) return rc;
     }
@@ -878,7 +878,7 @@ int mm_multi_create(int n_gpus, const int *devices, mm_multi **out) {
     return fail(MM_ERR_CUDA, std::string("no CUDA device available: ") +
                                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
   }
-  if (n_gpus > count) {
+  if (!devices && n_gpus > count) {  // an explicit list may name a device more than once (tests do)
     return fail(MM_ERR_INVALID, "mm_multi_create: " + std::to_string(n_gpus) + " devices requested, " +
                                     std::to_string(count) + " visible");
   }

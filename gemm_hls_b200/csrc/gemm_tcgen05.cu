@@ -21,11 +21,14 @@
 //     reference's inputs are all positive (U[1,10], test/TestSimulation.cpp:46-55), so truncation
 //     would bias every product by about -2^-11 * 2 and land the sum right at the 1e-3 tolerance.
 //     A and B are therefore rounded to nearest TF32 (cvt.rna.tf32.f32) into scratch copies first.
-//   * B's rounding runs CONCURRENTLY with the GEMM: a co-resident persistent kernel on a second
-//     stream rounds B panel by panel (BLOCK_N columns x all of K, in the order the rasterisation
-//     consumes panels) and publishes each panel through a counter; the GEMM's producer waits for a
-//     panel's counter before its first TMA load from it.  The same pass can read row-slices of B
-//     from PEER GPUs (multi-GPU host path): the NVLink all-gather of B is fused into it.
+//   * B's preparation CAN run concurrently with the GEMM (tuning knob b_overlap): a co-resident
+//     persistent kernel on a second stream prepares B panel by panel (BLOCK_N columns x all of K, in
+//     the order the rasterisation consumes panels) and publishes each panel through a counter; the
+//     GEMM's producer waits for a panel's counter before its first TMA load from it.  For the LOCAL
+//     rounding pass this is off by default: measured (profiles/r02_exp_b_overlap.md) the HBM-bound pass
+//     slows the co-running, latency-sensitive GEMM by more than it hides (1.83 vs 1.64 ms per step on a
+//     2048-row block, 11.38 vs 10.97 ms at 16384^3).  The same pass (overlapped or not) reads row-slices
+//     of B from PEER GPUs in the multi-GPU host path: the NVLink all-gather of B is fused into it.
 //   * half needs no preparation at all: A is K-major as stored, B is read MN-major in place.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -337,7 +340,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tcgen05_fence_after_sync();
           const uint64_t adesc = ptx::make_smem_desc_k_sw128(smem_a0 + stage * G::A_STAGE_BYTES);
-          const uint64_t bdesc = BMN ? ptx::make_smem_desc_mn_sw128(smem_b0 + stage * G::B_STAGE_BYTES, MN_ATOM_BYTES)
+          // MN-major B: 16-bit types swizzle 16-byte chunks over 8 k-rows (layout type 2, SBO 1024 B); tf32 has
+          // only the 32-byte-chunk mode over 4 k-rows (layout type 1, SBO 512 B) — see ptx_sm100.cuh
+          const uint64_t bdesc = BMN ? ptx::make_smem_desc_mn(smem_b0 + stage * G::B_STAGE_BYTES, MN_ATOM_BYTES,
+                                                              ELEM_BYTES == 4 ? 512u : 1024u, ELEM_BYTES == 4 ? 1u : 2u)
                                      : ptx::make_smem_desc_k_sw128(smem_b0 + stage * G::B_STAGE_BYTES);
           // K-major: advancing K inside the swizzle atom = advancing the start address by 32 B;
           // MN-major: one UMMA_K is UMMA_K_ELEMS k-rows of 128 B.
@@ -644,8 +650,9 @@ int make_operand_map(CUtensorMap *map, const void *base, int dtype, uint64_t row
 // MN-major B operand read from row-major B (K x M): box = {one 128-byte atom of columns, BLOCK_K k-rows}.
 int make_b_mn_map(CUtensorMap *map, const void *base, int dtype, uint64_t k, uint64_t m) {
   const uint32_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  // tf32: tcgen05 reads MN-major 32-bit operands only in the 32-byte-chunk swizzle (SWIZZLE_128B_BASE32B)
   return encode(map, tma_dtype(dtype), base, m, k, m * eb, 128 / eb, uint32_t(BLOCK_K_BYTES / eb),
-                CU_TENSOR_MAP_SWIZZLE_128B, "MN-major B");
+                eb == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, "MN-major B");
 }
 
 // C (row-major rows x m) for the epilogue's TMA stores: 32 x 32 blocks, swizzle = row pitch of the block.
@@ -752,6 +759,16 @@ int tcgen05_prepare_b(int dtype, const BSource &src, void *bt, unsigned k, unsig
     // co-resident persistent grid (one 512-thread CTA per SM next to the GEMM's CTA) when the GEMM
     // consumes panels while this runs; a wider grid when it runs alone in stream order
     const int grid = publish ? num_sms() : num_sms() * 2;
+    // An SM changes its L1 / shared-memory split only when it is idle.  This kernel uses no shared memory; were it
+    // to run under the default (L1-heavy) split, the GEMM's CTAs (214 KiB of shared memory) could not become
+    // resident next to it and would wait for it to END — measured: the "overlapped" GEMM took exactly its own time
+    // plus this kernel's.  Ask for the shared-memory-heavy split so that both fit on an SM together.
+    // (Function attributes are per device: set on every call, it is cheap.  A's rounding kernel may share SMs with
+    // this one, so it asks for the same split — tcgen05_prepare_a.)
+    MM_CUDA_TRY(cudaFuncSetAttribute(prep_b_panels_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+    MM_CUDA_TRY(cudaFuncSetAttribute(prep_b_panels_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
     return launch_panels(!in_place, src, bt, eb, k, m, panel_cols, publish ? ready : nullptr, grid, stream);
   }
   // K-major copy B^T (M x K): tuning knob b_mn = 0, and always for the 3xTF32 split
@@ -801,6 +818,8 @@ int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsi
       }
       *a_op = aprep;
     } else if (!t.tf32_no_round()) {
+      MM_CUDA_TRY(cudaFuncSetAttribute(round_tf32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));  // see tcgen05_prepare_b
       const size_t count4 = size_t(rows) * k / 4;
       const int blocks = int(std::min<size_t>((count4 + 255) / 256, size_t(num_sms()) * 16));
       round_tf32_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float4 *>(a),

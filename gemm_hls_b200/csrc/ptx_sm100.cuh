@@ -230,17 +230,21 @@ __device__ __forceinline__ uint64_t make_smem_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// MN-major operand (element (mn, k) at mn contiguous): stored as 64-element (128-byte) wide atoms of
-// `k` rows x 128 B with the 128-byte swizzle — what a TMA box {64 elements of MN, k rows} writes.
-// Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = byte distance between
-// consecutive 64-element MN atoms, SBO = 1024 B between groups of 8 k-rows.
-__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+// MN-major operand (element (mn, k) with mn contiguous): 128-byte wide atoms of k-rows x 128 B, what a TMA
+// box {128 B of MN, k rows} writes.  Canonical layouts (cute/atom/mma_traits_sm100.hpp):
+//   16-bit types:  SWIZZLE_128B (layout type 2): 16-byte chunks swizzled over 8 k-rows,
+//                  ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> SBO = 1024 B between 8-row groups
+//   32-bit types (tf32): the ONLY MN-major mode is SWIZZLE_128B_BASE32B (layout type 1): 32-byte chunks
+//                  swizzled over 4 k-rows (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) -> SBO = 512 B
+// LBO = byte distance between consecutive 128-byte MN atoms.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                      uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
-  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 

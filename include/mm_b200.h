@@ -196,7 +196,8 @@ enum {
   MM_TUNE_TCGEN05_B_MN = 5,        /* 0 | 1: read B MN-major from its row-major layout (1) or K-major
                                       from a transposed copy (0)                                      MM_TCGEN05_B_MN */
   MM_TUNE_TCGEN05_L2_POLICY = 6,   /* TMA loads' L2 eviction priority: 0 normal, 1 first, 2 last       MM_TCGEN05_L2 */
-  MM_TUNE_TCGEN05_B_OVERLAP = 7,   /* 0 | 1: prepare float B concurrently with the GEMM (default 1)    MM_TCGEN05_B_OVERLAP */
+  MM_TUNE_TCGEN05_B_OVERLAP = 7,   /* 0 | 1: prepare B concurrently with the GEMM that consumes it panel by
+                                      panel (default 0: measured slower, profiles/r02_exp_b_overlap.md) MM_TCGEN05_B_OVERLAP */
   MM_TUNE_TCGEN05_TMA_STORE = 8,   /* 0 | 1: epilogue through shared memory + TMA stores (default 1)   MM_TCGEN05_TMA_STORE */
   MM_TUNE_DMMA_TILE_ROWS = 9,      /* 0 = automatic | 64 | 128: CTA tile rows of the double kernel     MM_DMMA_TILE_ROWS */
   MM_TUNE_EXPERIMENT_TF32_NO_ROUND = 10, /* 1: feed raw fp32 bits to kind::tf32 (measures the truncation

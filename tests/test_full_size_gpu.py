@@ -20,6 +20,9 @@ def _launch(mm, ctx, torch, dt, mp, rd, a, b, c, flags=0):
     n, k = a.shape
     m = b.shape[1]
     s = torch.cuda.current_stream()
+    # the context's own stream is non-blocking: it does not wait for torch's pending work (the kernels that
+    # generate A and B, or an earlier fill of C) unless the device is idle first
+    torch.cuda.synchronize()
     ctx.enqueue(dt, mp, rd, a.data_ptr(), b.data_ptr(), c.data_ptr(), n, k, m, flags=flags,
                 stream=s.cuda_stream if s.cuda_stream else None)
     torch.cuda.synchronize()

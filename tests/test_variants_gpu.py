@@ -304,6 +304,33 @@ def test_multi_gemm_host_equals_single_context(mm, oracle, gpus, dt, mp, rd, n, 
             assert 0 < sec_dev <= sec_wall
 
 
+def _real_devices():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_real_devices() < 2, reason="needs two GPUs (run with gpurun --gpus 2; log in profiles/)")
+@pytest.mark.parametrize("dt,mp,rd,n,k,m", MULTI_CASES + [("FLOAT", "MULTIPLY", "ADD", 4096, 2048, 4096),
+                                                          ("HALF", "MULTIPLY", "ADD", 2048, 4096, 2048)])
+def test_multi_gemm_host_over_nvlink(mm, oracle, dt, mp, rd, n, k, m):
+    """The same check on DISTINCT devices: B's slices cross NVLink (peer loads in the gather kernel)."""
+    dtype, m_, r_ = getattr(mm, dt), getattr(mm, mp), getattr(mm, rd)
+    gpus = min(_real_devices(), 8)
+    a, b = half_inputs(oracle, n, k, m) if dt == "HALF" else oracle.fill(dtype, n, k, m, 19)
+    single = mm.matrix_multiplication_kernel(a, b, n, k, m, dtype=dtype, map_op=m_, reduce_op=r_)
+    with mm.Multi(gpus) as multi:
+        assert multi.peer_access
+        for rep in range(2):
+            c, _, _ = multi.gemm_host(dtype, m_, r_, a, b, n, k, m)
+            assert c.tobytes() == single.tobytes(), (gpus, rep)
+        multi.upload(dtype, a, b, n, k, m)
+        multi.execute(dtype, m_, r_, n, k, m)
+        assert multi.download(dtype, n, m).tobytes() == single.tobytes()
+
+
 def test_multi_more_gpus_than_rows_or_slices(mm, oracle):
     n, k, m = 3, 64, 64          # 4 "GPUs": one has no rows; K has a single 64-row slice
     a, b = oracle.fill(oracle.FLOAT, n, k, m, 23)
