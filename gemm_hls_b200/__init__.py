@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmm_b200.so")
+# MM_B200_LIB: A/B experiments load a variant build (scripts/build_semiring_variants.sh); the product is the in-tree library
+LIB_PATH = os.environ.get("MM_B200_LIB") or os.path.join(HERE, "libmm_b200.so")
 
 # MM_DATA_TYPE codes
 HALF, FLOAT, DOUBLE, INT32, UINT32, UINT8 = range(6)

@@ -6,10 +6,14 @@ reference's own communication-volume model  Q = N*M*(1 + K/T_N + K/T_M)  element
 (src/PrintSpecifications.cpp:72-78) evaluated for the PATCH of C that co-running tiles share through
 L2 (T_N = rasterisation-group rows, T_M = co-running column extent).
 
-    python scripts/tile_sweep.py --workload half32768 --out gpurun_out/r01/tile_sweep_half32768.csv
+    python scripts/tile_sweep.py --workload half32768 --out gpurun_out/r02_tile_sweep_half32768.csv
 
-Swept: CTA group (1 | 2 = cta_group::2 pairs), ring depth, rasterisation-group rows.
-Each configuration runs in its own process (the knobs are environment variables read once).
+Where the reference rebuilds the bitstream per configuration (MM_PARALLELISM_*, MM_MEMORY_TILE_SIZE_*,
+scripts/build_manager.py:224-306), every variant here is compiled into libmm_b200.so and selected per context
+(mm_context_set_tuning; bench.py --tune).  Swept: CTA group (1 | 2 = cta_group::2 pairs), C tile columns
+(UMMA N = 128 | 256), ring depth, rasterisation-group rows, epilogue route (TMA stores | direct), B layout
+(MN-major in place | K-major copy).  Every configuration passes bench.py's on-device result check before its
+line is written (column `verified`); the parity suite proper runs the same knobs (tests/test_variants_gpu.py).
 """
 import argparse
 import csv
@@ -23,22 +27,24 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHAPES = {"half32768": (32768, 2), "float16384": (16384, 4), "half16384": (16384, 2)}
 
 
-def run_bench(workload, env, steps):
-    e = dict(os.environ)
-    e.update(env)
+def tune_arg(cfg):
+    return ",".join("%s=%d" % kv for kv in sorted(cfg.items()))
+
+
+def run_bench(workload, cfg, steps):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", str(steps),
-                        "--warmup", "3", "--no-e2e", "--no-cpu"], capture_output=True, text=True, env=e, timeout=900)
+                        "--warmup", "3", "--no-e2e", "--no-cpu", "--tune", tune_arg(cfg)], capture_output=True, text=True,
+                       timeout=900)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
-    return json.loads(lines[-1]) if lines else None
+    return json.loads(lines[-1]) if (lines and r.returncode == 0) else None   # non-zero: the result check failed
 
 
-def run_ncu(workload, env):
+def run_ncu(workload, cfg):
     e = dict(os.environ)
-    e.update(env)
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct",
            "--clock-control", "none", "-k", "regex:gemm_tcgen05", "-s", "1", "-c", "1", "--csv",
            sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", "1", "--warmup", "3",
-           "--no-e2e", "--no-cpu"]
+           "--no-e2e", "--no-cpu", "--tune", tune_arg(cfg)]
     r = subprocess.run(cmd, capture_output=True, text=True, env=e, timeout=900)
     vals = {}
     for row in csv.reader(l for l in r.stdout.splitlines() if l.startswith('"')):
@@ -56,38 +62,49 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tile_sweep.csv"))
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the DRAM-traffic capture (faster)")
     args = ap.parse_args()
     size, eb = SHAPES.get(args.workload, (16384, 4))
+    base = dict(cta_group=2, block_n=256, stages=0, raster_rows=2048, tma_store=1, b_mn=1)
     if args.quick:
-        grid = [(2, 4, 2048), (1, 4, 2048)]
+        grid = [dict(base), dict(base, cta_group=1)]
     else:
-        grid = [(cg, st, rr) for cg, st, rr in itertools.product((1, 2), (3, 4, 5, 6), (2048,)) if not (cg == 1 and st > 4)]
-        grid += [(2, 4, rr) for rr in (256, 512, 1024, 4096, 8192)]
+        grid = []
+        for cg, bn in ((2, 256), (1, 256), (2, 128), (1, 128)):
+            deepest = {(2, 256): 6, (1, 256): 4, (2, 128): 8, (1, 128): 6}[(cg, bn)]
+            for st in sorted({3, 4, deepest}):
+                if st <= deepest:
+                    grid.append(dict(base, cta_group=cg, block_n=bn, stages=st))
+        grid += [dict(base, raster_rows=rr) for rr in (256, 512, 1024, 4096, 8192)]
+        grid += [dict(base, tma_store=0), dict(base, b_mn=0), dict(base, tile_sync=0)]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow(["config", "time", "performance", "cta_group", "stages", "raster_rows", "dram_bytes",
-                    "model_bytes", "l2_hit_pct", "sm_mhz"])
-        for cg, st, rr in grid:
-            env = {"MM_TCGEN05_CTA_GROUP": str(cg), "MM_TCGEN05_STAGES": str(st), "MM_TCGEN05_RASTER_ROWS": str(rr)}
-            d = run_bench(args.workload, env, args.steps)
-            t = run_ncu(args.workload, env)
+        w.writerow(["config", "time", "performance", "cta_group", "block_n", "stages", "raster_rows", "tma_store", "b_mn",
+                    "verified", "dram_bytes", "model_bytes", "l2_hit_pct", "sm_mhz"])
+        for cfg in grid:
+            cg, bn, rr = cfg["cta_group"], cfg["block_n"], cfg["raster_rows"]
+            d = run_bench(args.workload, cfg, args.steps)
+            name = "%s_%s" % (args.workload, tune_arg({k: v for k, v in cfg.items() if base.get(k) != v}) or "default")
             if d is None:
+                w.writerow([name, "", "", cg, bn, cfg["stages"], rr, cfg["tma_store"], cfg["b_mn"], "FAILED", "", "", "", ""])
+                print(name, "FAILED", flush=True)
                 continue
+            t = run_ncu(args.workload, cfg) if not args.no_ncu else {}
             # patch shared through L2: rr rows x (co-running tiles / row-tiles-per-group) column tiles
             tile_rows = 128 * cg
             groups = 148 // cg
             rows_tiles = max(1, min(rr, size) // tile_rows)
             t_n = rows_tiles * tile_rows
-            t_m = max(256.0, groups / rows_tiles * 256.0)
+            t_m = max(float(bn), groups / rows_tiles * float(bn))
             model = eb * size * size * (1 + size / t_n + size / min(t_m, size))
             r = d["roofline"]
             dram = t.get("dram__bytes_read.sum", 0) + t.get("dram__bytes_write.sum", 0)
-            w.writerow(["%s_cg%d_s%d_r%d" % (args.workload, cg, st, rr), "%.6f" % (1e-3 * r["kernel_ms"]),
-                        "%.1f" % (1e3 * r["achieved"]), cg, st, rr, int(dram), int(model),
+            w.writerow([name, "%.6f" % (1e-3 * r["kernel_ms"]), "%.1f" % (1e3 * r["achieved"]), cg, bn, cfg["stages"], rr,
+                        cfg["tma_store"], cfg["b_mn"], "yes" if d.get("check") else "n/a", int(dram), int(model),
                         "%.1f" % t.get("lts__t_sector_hit_rate.pct", float("nan")), d["clocks"]["sm_mhz"]])
             f.flush()
-            print(cg, st, rr, "%.3f ms" % r["kernel_ms"], "%.0f GOp/s" % (1e3 * r["achieved"]),
+            print(name, "%.3f ms" % r["kernel_ms"], "%.0f GOp/s" % (1e3 * r["achieved"]),
                   "dram %.1f GB (model %.1f GB)" % (dram * 1e-9, model * 1e-9), flush=True)
 
 
