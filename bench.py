@@ -35,6 +35,7 @@ WORKLOADS = {
     "half32768": ("half", "Multiply", "Add", 32768, 32768, 32768, "configs[2] half 32768^3"),
     "double8192": ("double", "Multiply", "Add", 8192, 8192, 8192, "configs[3] double 8192^3"),
     "addmin8192": ("float", "Add", "Min", 8192, 8192, 8192, "configs[4] (add,min) float 8192^3"),
+    "uint8_16384": ("uint8_t", "Multiply", "Add", 16384, 16384, 16384, "SURVEY.md 8(f3): uint8_t on tcgen05 kind::i8"),
     "float4096": ("float", "Multiply", "Add", 4096, 4096, 4096, "reduced size, debugging only"),
 }
 DEFAULT_WORKLOAD = "float16384"
@@ -164,7 +165,7 @@ def reference_naive_sample(dtype_name, mp_name, rd_name, a_rows, b, k, m, thread
     (ctypes releases the GIL during the call).  Returns (wall seconds, kind, threads used)."""
     from concurrent.futures import ThreadPoolExecutor
     import oracle as O
-    dt = {"float": O.FLOAT, "half": O.HALF, "double": O.DOUBLE}[dtype_name]
+    dt = {"float": O.FLOAT, "half": O.HALF, "double": O.DOUBLE, "uint8_t": O.UINT8}[dtype_name]
     mp, rd = getattr(O, mp_name.upper()), getattr(O, rd_name.upper())
     rows = a_rows.shape[0]
     threads = max(1, min(threads, rows))
@@ -262,10 +263,10 @@ def main():
                             "prepares, every step) its A row-block and its B column-block; no collective inside a step"
                             % (grid_r, grid_c, args.gpus, grid_r, grid_c)),
               "l2": "inputs (A+B+C = %.2f GB) far larger than the 126 MB L2; no explicit flush" %
-                    (1e-9 * {"float": 4, "half": 2, "double": 8}[dtype_name] * (N * K + K * M + N * M))}
+                    (1e-9 * {"float": 4, "half": 2, "double": 8, "uint8_t": 1}[dtype_name] * (N * K + K * M + N * M))}
 
     import numpy as np
-    np_dt = {"float": np.float32, "half": np.float16, "double": np.float64}[dtype_name]
+    np_dt = {"float": np.float32, "half": np.float16, "double": np.float64, "uint8_t": np.uint8}[dtype_name]
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -311,7 +312,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         host_group = dist.new_group(backend="gloo")  # CPU-side barrier: ranks that wait must not spin on their GPU
 
-    t_dt = {"float": torch.float32, "half": torch.float16, "double": torch.float64}[dtype_name]
+    t_dt = {"float": torch.float32, "half": torch.float16, "double": torch.float64, "uint8_t": torch.uint8}[dtype_name]
     dtype = G.DTYPE_FROM_NAME[dtype_name]
     mp, rd = G.OP_FROM_NAME[mp_name], G.OP_FROM_NAME[rd_name]
     es = torch.empty((), dtype=t_dt).element_size()
@@ -321,7 +322,7 @@ def main():
     # over a grid_r x grid_c grid of ranks: rank (i, j) computes rows block i x columns block j from A's row-block i and
     # B's column-block j.  grid_c = 1 is SURVEY.md 8e's row-block split with B replicated; a 2-D grid replicates less
     # operand preparation per step (each rank rounds 1/grid_r of A and 1/grid_c of B instead of all of B).
-    w = {"float": 16, "half": 32, "double": 8}[dtype_name]           # columns stay multiples of the 64-byte memory word
+    w = {"float": 16, "half": 32, "double": 8, "uint8_t": 64}[dtype_name]   # columns stay multiples of the 64-byte memory word
     r0, r1, c0, c1 = partition.rank_block(rank, (grid_r, grid_c), N, M, w)
     n_local, m_local = r1 - r0, c1 - c0
 
@@ -329,10 +330,16 @@ def main():
     gen.manual_seed(5 + rank)
     # synthetic U[1,10) inputs as in the reference recipe (test/TestSimulation.cpp:46-55); half uses
     # U[0,1) so that C stays finite in half (SURVEY.md trap 5)
-    lo, hi = (0.0, 1.0) if dtype_name == "half" else (1.0, 10.0)
-    a_blk = (torch.rand((n_local, K), generator=gen, device=dev, dtype=torch.float32) * (hi - lo) + lo).to(t_dt)
+    lo, hi = (0.0, 1.0) if dtype_name == "half" else ((0.0, 256.0) if dtype_name == "uint8_t" else (1.0, 10.0))
+
+    def draw(shape, g):   # uint8_t: the full value range, so that the modulo-256 wrap-around is exercised
+        if dtype_name == "uint8_t":
+            return torch.randint(0, 256, shape, generator=g, device=dev, dtype=torch.uint8)
+        return (torch.rand(shape, generator=g, device=dev, dtype=torch.float32) * (hi - lo) + lo).to(t_dt)
+
+    a_blk = draw((n_local, K), gen)
     if rank == 0:
-        b_full = (torch.rand((K, M), generator=gen, device=dev, dtype=torch.float32) * (hi - lo) + lo).to(t_dt)
+        b_full = draw((K, M), gen)
     else:
         b_full = torch.empty((K, M), device=dev, dtype=t_dt)
     extra = {}
@@ -410,6 +417,10 @@ def main():
     # ---- light on-device sanity so that a wrong kernel cannot post a number (not the parity test)
     def check_rows(got_rows, a_rows_t, what, b_t=None):
         ref = a_rows_t.double() @ (b_full if b_t is None else b_t).double()
+        if dtype_name == "uint8_t":   # exact: FP64 holds the integer sums (< 2^53); the reference stores them modulo 256
+            if not torch.equal(torch.remainder(ref, 256.0), got_rows.double()):
+                raise SystemExit("bench.py: %s result check failed (uint8_t rows differ from the exact sums modulo 256)" % what)
+            return 0.0
         rel = ((got_rows.double() - ref).abs() / ref.abs().clamp_min(1e-30)).max().item()
         tol = 1e-2 if dtype_name == "half" else 1e-3
         if not (rel <= tol):
@@ -427,14 +438,16 @@ def main():
         path = G.kernel_path(dtype, mp, rd, flags)
         main_avg_s = main_s / max(calls, 1)
         local_ops = 2.0 * n_local * K * m_local
-        if path in ("tcgen05_tf32", "tcgen05_f16"):
+        if path in ("tcgen05_tf32", "tcgen05_f16", "tcgen05_i8"):
             # burst figure when the whole timed region is shorter than the ~1 s it takes the power
             # cap to pull the clocks down, the sustained one for a seconds-long back-to-back loop
             long_run = elapsed_ms > 1500.0
             peak_bf16 = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) if long_run else peaks["bf16_tflops"]
-            peak = peak_bf16 / 2.0 if path == "tcgen05_tf32" else peak_bf16
+            peak = {"tcgen05_tf32": peak_bf16 / 2.0, "tcgen05_f16": peak_bf16, "tcgen05_i8": peak_bf16 * 2.0}[path]
             peak_note = ("%s bf16 %s %.1f TF/s%s" % (peaks["_source"], "sustained" if long_run else "burst", peak_bf16,
-                         " / 2 (kind::tf32 issues at half the 16-bit rate)" if path == "tcgen05_tf32" else ""))
+                         {"tcgen05_tf32": " / 2 (kind::tf32 issues at half the 16-bit rate)", "tcgen05_f16": "",
+                          "tcgen05_i8": " x 2 (kind::i8 issues at twice the 16-bit rate; no measured int8 figure in "
+                                        "MEASURED_PEAKS.json)"}[path]))
             roof = {"bound": "tensor", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TFLOP/s"}
         elif path == "dmma_f64":
             # FP64 DMMA is not in MEASURED_PEAKS.json.  Measured on this pool with a registers-only DMMA loop
@@ -467,7 +480,8 @@ def main():
         out = {"metric": metric_name, "value": value, "unit": metric, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": {"float": "tf32 tensor-core multiply, f32 accumulate/storage",
-                                              "half": "f16 multiply, f32 accumulate", "double": "f64"}[dtype_name]
+                                              "half": "f16 multiply, f32 accumulate", "double": "f64",
+                                              "uint8_t": "u8 multiply, s32 accumulate, low byte stored (= the reference's arithmetic modulo 256)"}[dtype_name]
                if (mp_name, rd_name) == ("Multiply", "Add") else "f32",
                "data": "synthetic", "config": config, "clocks": clocks, "roofline": roof,
                # NVML board power during the timed region (the reference's PSU power meter)
@@ -496,8 +510,7 @@ def main():
             g2.manual_seed(99)
             for i in range(0, N, 2048):   # the other ranks' row-blocks are synthetic too: draw all of A here
                 rows_i = min(2048, N - i)
-                blk = (torch.rand((rows_i, K), generator=g2, device=dev, dtype=torch.float32) * (hi - lo) + lo).to(t_dt)
-                a_host[i:i + rows_i].copy_(blk)
+                a_host[i:i + rows_i].copy_(draw((rows_i, K), g2))
             b_host.copy_(b_full)
             torch.cuda.synchronize()
             a_np, b_np, c_np = a_host.numpy(), b_host.numpy(), c_host.numpy()

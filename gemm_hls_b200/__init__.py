@@ -35,11 +35,12 @@ OP_FROM_NAME = {"Multiply": MULTIPLY, "Product": MULTIPLY, "Add": ADD, "Sum": AD
 
 # MM_TUNE_* knobs (include/mm_b200.h)
 (TUNE_CTA_GROUP, TUNE_BLOCK_N, TUNE_STAGES, TUNE_RASTER_ROWS, TUNE_TILE_SYNC, TUNE_B_MN, TUNE_L2_POLICY,
- TUNE_B_OVERLAP, TUNE_TMA_STORE, TUNE_DMMA_TILE_ROWS, TUNE_EXPERIMENT_TF32_NO_ROUND) = range(11)
+ TUNE_B_OVERLAP, TUNE_TMA_STORE, TUNE_DMMA_TILE_ROWS, TUNE_EXPERIMENT_TF32_NO_ROUND, TUNE_SEMIRING_RING) = range(12)
 TUNE_NAMES = {"cta_group": TUNE_CTA_GROUP, "block_n": TUNE_BLOCK_N, "stages": TUNE_STAGES,
               "raster_rows": TUNE_RASTER_ROWS, "tile_sync": TUNE_TILE_SYNC, "b_mn": TUNE_B_MN,
               "l2_policy": TUNE_L2_POLICY, "b_overlap": TUNE_B_OVERLAP, "tma_store": TUNE_TMA_STORE,
-              "dmma_tile_rows": TUNE_DMMA_TILE_ROWS, "tf32_no_round": TUNE_EXPERIMENT_TF32_NO_ROUND}
+              "dmma_tile_rows": TUNE_DMMA_TILE_ROWS, "tf32_no_round": TUNE_EXPERIMENT_TF32_NO_ROUND,
+              "semiring_ring": TUNE_SEMIRING_RING}
 
 EXPORTS = ["mm_last_error", "mm_version", "mm_dtype_size", "mm_memory_width", "mm_context_create",
            "mm_context_destroy", "mm_buffer_alloc", "mm_buffer_free", "mm_copy_to_device",

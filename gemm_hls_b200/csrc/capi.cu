@@ -37,7 +37,7 @@ const KnobInfo kKnobs[MM_TUNE_COUNT] = {
     {"MM_TCGEN05_CTA_GROUP", 2}, {"MM_TCGEN05_BLOCK_N", 256},  {"MM_TCGEN05_STAGES", 0},
     {"MM_TCGEN05_RASTER_ROWS", 2048}, {"MM_TCGEN05_TILE_SYNC", 1}, {"MM_TCGEN05_B_MN", 1},
     {"MM_TCGEN05_L2", 0}, {"MM_TCGEN05_B_OVERLAP", 0}, {"MM_TCGEN05_TMA_STORE", 1},
-    {"MM_DMMA_TILE_ROWS", 0}, {"MM_EXPERIMENT_TF32_NO_ROUND", 0},
+    {"MM_DMMA_TILE_ROWS", 0}, {"MM_EXPERIMENT_TF32_NO_ROUND", 0}, {"MM_SEMIRING_RING", 1},
 };
 
 }  // namespace
@@ -55,7 +55,8 @@ int tuning_validate(int knob, int value) {
     case MM_TUNE_TCGEN05_B_MN:
     case MM_TUNE_TCGEN05_B_OVERLAP:
     case MM_TUNE_TCGEN05_TMA_STORE:
-    case MM_TUNE_EXPERIMENT_TF32_NO_ROUND: ok = value == 0 || value == 1; break;
+    case MM_TUNE_EXPERIMENT_TF32_NO_ROUND:
+    case MM_TUNE_SEMIRING_RING: ok = value == 0 || value == 1; break;
     default: return fail(MM_ERR_INVALID, "unknown tuning knob " + std::to_string(knob));
   }
   if (!ok) {
@@ -113,9 +114,14 @@ bool valid_op(int o) { return o >= 0 && o < MM_OP_COUNT; }
 
 enum Path { kPathTcgen05, kPathDmma, kPathSemiring };
 
-Path select_path(int dtype, int map_op, int reduce_op, int flags, unsigned n) {
+// uint8_t on tcgen05 kind::i8: products accumulate exactly in 32-bit integers while 255^2 * K < 2^31; the low byte
+// of the exact sum is the reference's modulo-256 arithmetic.  Longer K takes the CUDA-core kernel.
+constexpr unsigned kMaxKInt8Tensor = 33024;
+
+Path select_path(int dtype, int map_op, int reduce_op, int flags, unsigned n, unsigned k) {
   const bool dense = (map_op == MM_OP_MULTIPLY && reduce_op == MM_OP_ADD) && !(flags & MM_FLAG_EXACT);
   if (dense && (dtype == MM_DTYPE_FLOAT || dtype == MM_DTYPE_HALF)) return kPathTcgen05;
+  if (dense && dtype == MM_DTYPE_UINT8 && k <= kMaxKInt8Tensor) return kPathTcgen05;
   if (dense && dtype == MM_DTYPE_DOUBLE) {
     // the DMMA kernel reads a transposed A through 16-byte boxes: needs an even N
     return ((flags & MM_FLAG_TRANSPOSED_A) && (n % 2 != 0)) ? kPathSemiring : kPathDmma;
@@ -202,7 +208,7 @@ int enqueue_locked(mm_context *ctx, int dtype, int map_op, int reduce_op, int fl
     MM_CUDA_TRY(cudaEventRecord(pe[0], stream));
   }
   int rc_launch = MM_OK;
-  switch (select_path(dtype, map_op, reduce_op, flags, n)) {
+  switch (select_path(dtype, map_op, reduce_op, flags, n, k)) {
     case kPathTcgen05: {
       const size_t need = mm::tcgen05_scratch_bytes(dtype, n, k, m, flags, ctx->tuning);
       if (need > ctx->scratch.bytes && capture != cudaStreamCaptureStatusNone) {
@@ -519,7 +525,7 @@ int multi_gemm_host_locked(mm_multi *mu, int dtype, int map_op, int reduce_op, i
     p = Pipeline{mu->ctx[g], dtype, map_op, reduce_op, flags,
                  static_cast<const unsigned char *>(a) + size_t(r0) * k * es, static_cast<const unsigned char *>(b),
                  static_cast<unsigned char *>(c) + size_t(r0) * m * es, r1 - r0, k, m, es,
-                 select_path(dtype, map_op, reduce_op, flags, std::max(1u, r1 - r0))};
+                 select_path(dtype, map_op, reduce_op, flags, std::max(1u, r1 - r0), k)};
     BPlan &bp = plans[g];
     if (mu->peer) {
       bp.k0 = std::min(k, unsigned(g) * part_rows);
@@ -684,7 +690,7 @@ int mm_context_reserve(mm_context *ctx, int dtype, int flags, unsigned n, unsign
   if (!valid_dtype(dtype)) return fail(MM_ERR_INVALID, "unknown MM_DATA_TYPE code");
   std::lock_guard<std::mutex> lock(ctx->mutex);
   MM_CUDA_TRY(cudaSetDevice(ctx->device));
-  if (dtype != MM_DTYPE_FLOAT && dtype != MM_DTYPE_HALF) return MM_OK;  // only the tcgen05 path keeps scratch
+  if (dtype != MM_DTYPE_FLOAT && dtype != MM_DTYPE_HALF && dtype != MM_DTYPE_UINT8) return MM_OK;  // only the tcgen05 path keeps scratch
   return ensure(ctx, ctx->scratch, mm::tcgen05_scratch_bytes(dtype, n, k, m, flags & ~MM_FLAG_EXACT, ctx->tuning),
                 ctx->captured);
 }
@@ -801,7 +807,7 @@ int mm_context_profile_read(mm_context *ctx, double *prep_sum, double *main_sum,
 int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags) {
   if (!valid_dtype(dtype) || !valid_op(map_op) || !valid_op(reduce_op)) return -1;
   const mm::Tuning t = mm::default_tuning();
-  switch (select_path(dtype, map_op, reduce_op, flags, 2)) {
+  switch (select_path(dtype, map_op, reduce_op, flags, 2, 64)) {
     case kPathTcgen05:
       // [B preparation unless B is read in place] + [A preparation for float or transposed A] + GEMM
       return 1 + (mm::tcgen05_b_in_place(dtype, flags, t) ? 0 : 1) +
@@ -814,8 +820,8 @@ int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags) {
 
 const char *mm_kernel_path(int dtype, int map_op, int reduce_op, int flags) {
   if (!valid_dtype(dtype) || !valid_op(map_op) || !valid_op(reduce_op)) return "invalid";
-  switch (select_path(dtype, map_op, reduce_op, flags, 2)) {
-    case kPathTcgen05: return dtype == MM_DTYPE_FLOAT ? "tcgen05_tf32" : "tcgen05_f16";
+  switch (select_path(dtype, map_op, reduce_op, flags, 2, 64)) {
+    case kPathTcgen05: return dtype == MM_DTYPE_FLOAT ? "tcgen05_tf32" : (dtype == MM_DTYPE_UINT8 ? "tcgen05_i8" : "tcgen05_f16");
     case kPathDmma: return "dmma_f64";
     case kPathSemiring: return "semiring_simt";
   }
@@ -849,7 +855,7 @@ int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flag
   std::lock_guard<std::mutex> lock(ctx->mutex);
   Pipeline p{ctx, dtype, map_op, reduce_op, flags, static_cast<const unsigned char *>(a),
              static_cast<const unsigned char *>(b), static_cast<unsigned char *>(c), n, k, m, mm_dtype_size(dtype),
-             select_path(dtype, map_op, reduce_op, flags, n)};
+             select_path(dtype, map_op, reduce_op, flags, n, k)};
   BPlan bp;
   bp.k0 = 0;
   bp.k1 = k;

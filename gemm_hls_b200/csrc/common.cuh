@@ -49,6 +49,7 @@ struct Tuning {
   bool tma_store() const { return v[MM_TUNE_TCGEN05_TMA_STORE] != 0; }
   int dmma_tile_rows() const { return v[MM_TUNE_DMMA_TILE_ROWS]; }
   bool tf32_no_round() const { return v[MM_TUNE_EXPERIMENT_TF32_NO_ROUND] != 0; }
+  bool semiring_ring() const { return v[MM_TUNE_SEMIRING_RING] != 0; }
 };
 Tuning default_tuning();                                  // capi.cu
 int tuning_validate(int knob, int value);                 // MM_OK or MM_ERR_INVALID (message set)

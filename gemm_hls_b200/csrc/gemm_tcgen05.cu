@@ -1,7 +1,9 @@
-// Tensor-core path of the hot path for the dense (Multiply, Add) contraction on float and half:
+// Tensor-core path of the hot path for the dense (Multiply, Add) contraction on float, half and uint8_t:
 //   C[N x M] = A[N x K] * B[K x M]
 // B200 counterpart of the reference's PE chain + streamers (kernel/Compute.cpp:53-146,
-// kernel/Memory.cpp:58-438) for MM_MAP_OP=Multiply, MM_REDUCE_OP=Add, MM_DATA_TYPE in {float, half}.
+// kernel/Memory.cpp:58-438) for MM_MAP_OP=Multiply, MM_REDUCE_OP=Add, MM_DATA_TYPE in {float, half, uint8_t}
+// (uint8_t: kind::i8 with exact 32-bit integer accumulation, truncated to 8 bits in the epilogue = the reference's
+// arithmetic modulo 256, bit for bit; reference CMakeLists.txt:43-46).
 //
 // Structure (one persistent CTA per SM, warp-specialised, no CUTLASS):
 //   warp 0   TMA producer (the role of ReadA / ReadB / FeedB): cp.async.bulk.tensor of 128-byte-swizzled
@@ -129,6 +131,27 @@ __device__ __forceinline__ void store_chunk<__half>(__half *crow, const uint32_t
   }
 }
 
+// uint8_t: the accumulator is the exact 32-bit sum; its low byte is the reference's result (arithmetic modulo 256).
+__device__ __forceinline__ void pack_u8(const uint32_t (&v)[32], uint32_t (&p)[8]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    p[q] = (v[4 * q] & 0xFFu) | ((v[4 * q + 1] & 0xFFu) << 8) | ((v[4 * q + 2] & 0xFFu) << 16) | (v[4 * q + 3] << 24);
+  }
+}
+
+template <>
+__device__ __forceinline__ void store_chunk<unsigned char>(unsigned char *crow, const uint32_t (&v)[32], uint32_t col,
+                                                           uint32_t cols) {
+  uint32_t p[8];
+  pack_u8(v, p);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (col + 16 * j + 16 <= cols) {
+      *reinterpret_cast<uint4 *>(crow + col + 16 * j) = make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+    }
+  }
+}
+
 // Staged variant: lane = row of a 32 x 32 block; the block is written into shared memory in the
 // swizzled layout the C tensor map expects (row pitch 128 B with SWIZZLE_128B for float, 64 B with
 // SWIZZLE_64B for half: 16-byte chunk index XOR row bits), so the quarter-warp phases of the 128-bit
@@ -153,6 +176,17 @@ __device__ __forceinline__ void stage_chunk<__half>(uint32_t buf, uint32_t lane,
 #pragma unroll
   for (uint32_t j = 0; j < 4; ++j) {
     ptx::st_shared_v4(row + ((j ^ ((lane >> 1) & 3u)) << 4), p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+  }
+}
+
+template <>
+__device__ __forceinline__ void stage_chunk<unsigned char>(uint32_t buf, uint32_t lane, const uint32_t (&v)[32]) {
+  uint32_t p[8];
+  pack_u8(v, p);
+  const uint32_t row = buf + lane * 32u;   // 32-byte rows, SWIZZLE_32B: 16-byte chunk index XOR address bit 7
+#pragma unroll
+  for (uint32_t j = 0; j < 2; ++j) {
+    ptx::st_shared_v4(row + ((j ^ ((lane >> 2) & 1u)) << 4), p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
   }
 }
 
@@ -197,7 +231,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, TOut *__restrict__ C, const GemmParams p) {
   using G = Geo<CG, BN>;
-  constexpr int ELEM_BYTES = (KIND == ptx::KIND_TF32) ? 4 : 2;
+  constexpr int ELEM_BYTES = (KIND == ptx::KIND_TF32) ? 4 : (KIND == ptx::KIND_I8 ? 1 : 2);
   constexpr int BLOCK_K_ELEMS = BLOCK_K_BYTES / ELEM_BYTES;
   constexpr int MN_ATOM = 128 / ELEM_BYTES;                 // columns per MN-major swizzle atom (128 B)
   constexpr int MN_ATOM_BYTES = BLOCK_K_ELEMS * 128;        // one atom: BLOCK_K k-rows x 128 B
@@ -619,8 +653,10 @@ split3_transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, 
 
 // ---- host side -----------------------------------------------------------------------------------
 CUtensorMapDataType tma_dtype(int dtype) {
-  return dtype == MM_DTYPE_FLOAT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  return dtype == MM_DTYPE_FLOAT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (dtype == MM_DTYPE_UINT8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
 }
+uint32_t elem_bytes(int dtype) { return dtype == MM_DTYPE_FLOAT ? 4u : (dtype == MM_DTYPE_UINT8 ? 1u : 2u); }
 
 int encode(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
            uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle, const char *what) {
@@ -642,14 +678,14 @@ int encode(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint64_t 
 // K-major operand: `rows` rows of `k_elems` elements; box = {128 bytes of K, box_rows}, 128-byte
 // swizzle, out-of-bounds reads return zeros (neutral for (Multiply, Add) — SURVEY.md section 5 trap 3).
 int make_operand_map(CUtensorMap *map, const void *base, int dtype, uint64_t rows, uint64_t k_elems, uint32_t box_rows) {
-  const uint32_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  const uint32_t eb = elem_bytes(dtype);
   return encode(map, tma_dtype(dtype), base, k_elems, rows, k_elems * eb, uint32_t(BLOCK_K_BYTES / eb), box_rows,
                 CU_TENSOR_MAP_SWIZZLE_128B, "K-major operand");
 }
 
 // MN-major B operand read from row-major B (K x M): box = {one 128-byte atom of columns, BLOCK_K k-rows}.
 int make_b_mn_map(CUtensorMap *map, const void *base, int dtype, uint64_t k, uint64_t m) {
-  const uint32_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  const uint32_t eb = elem_bytes(dtype);
   // tf32: tcgen05 reads MN-major 32-bit operands only in the 32-byte-chunk swizzle (SWIZZLE_128B_BASE32B)
   return encode(map, tma_dtype(dtype), base, m, k, m * eb, 128 / eb, uint32_t(BLOCK_K_BYTES / eb),
                 eb == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, "MN-major B");
@@ -657,9 +693,9 @@ int make_b_mn_map(CUtensorMap *map, const void *base, int dtype, uint64_t k, uin
 
 // C (row-major rows x m) for the epilogue's TMA stores: 32 x 32 blocks, swizzle = row pitch of the block.
 int make_c_map(CUtensorMap *map, void *base, int dtype, uint64_t rows, uint64_t m) {
-  const uint32_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  const uint32_t eb = elem_bytes(dtype);
   return encode(map, tma_dtype(dtype), base, m, rows, m * eb, 32, 32,
-                eb == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "C");
+                eb == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : (eb == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), "C");
 }
 
 int num_sms() {
@@ -714,17 +750,17 @@ Tcgen05Counters tcgen05_counters(void *scratch, size_t scratch_bytes) {
 bool tcgen05_b_mn(int dtype, int flags, const Tuning &t) { return t.b_mn() && !split3(dtype, flags); }
 
 bool tcgen05_b_in_place(int dtype, int flags, const Tuning &t) {
-  return tcgen05_b_mn(dtype, flags, t) && (dtype == MM_DTYPE_HALF || t.tf32_no_round());
+  return tcgen05_b_mn(dtype, flags, t) && (dtype == MM_DTYPE_HALF || dtype == MM_DTYPE_UINT8 || t.tf32_no_round());
 }
 
 size_t tcgen05_bt_bytes(int dtype, unsigned k, unsigned m, int flags, const Tuning &t) {
   if (tcgen05_b_in_place(dtype, flags, t)) return 0;
-  const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  const size_t eb = elem_bytes(dtype);
   return align_up(size_t(m) * k * eb * (split3(dtype, flags) ? 3 : 1), 1024);
 }
 
 size_t tcgen05_scratch_bytes(int dtype, unsigned n, unsigned k, unsigned m, int flags, const Tuning &t) {
-  const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  const size_t eb = elem_bytes(dtype);
   size_t bytes = TAIL_BYTES + tcgen05_bt_bytes(dtype, k, m, flags, t);  // counters (tail) + B copy
   if (dtype == MM_DTYPE_FLOAT || (flags & MM_FLAG_TRANSPOSED_A)) {
     bytes += align_up(size_t(n) * k * eb * (split3(dtype, flags) ? 3 : 1), 1024);
@@ -744,7 +780,7 @@ int tcgen05_prepare_b(int dtype, const BSource &src, void *bt, unsigned k, unsig
   *b_op = bt;
   if (ready_target) *ready_target = 0;
   const bool parts = src.src != nullptr;
-  const size_t eb = (dtype == MM_DTYPE_FLOAT) ? 4 : 2;
+  const size_t eb = elem_bytes(dtype);
   if (tcgen05_b_mn(dtype, flags, t)) {
     const bool in_place = tcgen05_b_in_place(dtype, flags, t);
     if (in_place && !parts) {
@@ -783,6 +819,8 @@ int tcgen05_prepare_b(int dtype, const BSource &src, void *bt, unsigned k, unsig
     } else {
       launch_transpose<float, true>(b, bt, k, m, stream);
     }
+  } else if (dtype == MM_DTYPE_UINT8) {
+    launch_transpose<unsigned char, false>(b, bt, k, m, stream);
   } else {
     launch_transpose<__half, false>(b, bt, k, m, stream);
   }
@@ -827,7 +865,8 @@ int tcgen05_prepare_a(int dtype, const void *a, void *aprep, unsigned rows, unsi
       *a_op = aprep;
     }
   } else if (transposed) {
-    launch_transpose<__half, false>(a, aprep, k, rows, stream);
+    if (dtype == MM_DTYPE_UINT8) launch_transpose<unsigned char, false>(a, aprep, k, rows, stream);
+    else launch_transpose<__half, false>(a, aprep, k, rows, stream);
     *a_op = aprep;
   }
   MM_CUDA_TRY(cudaGetLastError());
@@ -899,7 +938,7 @@ int gemm_dispatch(int dtype, const void *a_op, const void *b_op, void *c, unsign
                   unsigned b_ready_target, bool attributes_only, cudaStream_t stream) {
   if (split3(dtype, flags)) k *= 3;  // the operands carry [hi|hi|lo] x [hi|lo|hi] per 16-block of K
   const bool is_f32 = dtype == MM_DTYPE_FLOAT;
-  const size_t eb = is_f32 ? 4 : 2;
+  const size_t eb = elem_bytes(dtype);
   const int cg = t.cta_group(), bn = t.block_n();
   const bool bmn = tcgen05_b_mn(dtype, flags, t);
   CUtensorMap map_a, map_b, map_c;
@@ -924,6 +963,11 @@ int gemm_dispatch(int dtype, const void *a_op, const void *b_op, void *c, unsign
   plan.p.l2_policy = t.l2_policy() == 1 ? ptx::L2_EVICT_FIRST : (t.l2_policy() == 2 ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL);
   plan.p.tile_sync = t.tile_sync() ? tile_sync : nullptr;
   plan.p.b_ready = b_ready;
+  if (dtype == MM_DTYPE_UINT8) {
+    // MN-major 8-bit atoms are 128 columns wide: a CTA must stage at least one (tile columns / CTAs per group >= 128)
+    if (bmn && bn / cg < 128) return dispatch_variant<ptx::KIND_I8, unsigned char>(cg, 256, bmn, plan);
+    return dispatch_variant<ptx::KIND_I8, unsigned char>(cg, bn, bmn, plan);
+  }
   return is_f32 ? dispatch_variant<ptx::KIND_TF32, float>(cg, bn, bmn, plan)
                 : dispatch_variant<ptx::KIND_F16, __half>(cg, bn, bmn, plan);
 }
@@ -945,7 +989,7 @@ int tcgen05_prepare_b_async(int dtype, const BSource &src, void *local_b, void *
   const bool parts = src.src != nullptr;
   if (parts && !tcgen05_b_mn(dtype, flags, t)) {
     // K-major copy requested (tuning / 3xTF32): assemble the slices first, then transpose locally
-    int rc = gather_b_rows(src, local_b, dtype == MM_DTYPE_FLOAT ? 4 : 2, k, m, stream);
+    int rc = gather_b_rows(src, local_b, elem_bytes(dtype), k, m, stream);
     if (rc != MM_OK) return rc;
     BSource whole;
     whole.b = local_b;
@@ -969,8 +1013,8 @@ int tcgen05_prepare_b_async(int dtype, const BSource &src, void *local_b, void *
 }
 
 int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_bytes) {
-  if (dtype != MM_DTYPE_FLOAT && dtype != MM_DTYPE_HALF) {
-    return fail(MM_ERR_UNSUPPORTED, "tcgen05 path handles float and half only");
+  if (dtype != MM_DTYPE_FLOAT && dtype != MM_DTYPE_HALF && dtype != MM_DTYPE_UINT8) {
+    return fail(MM_ERR_UNSUPPORTED, "tcgen05 path handles float, half and uint8_t only");
   }
   if (g.tuning == nullptr) return fail(MM_ERR_INVALID, "tcgen05 launch without tuning");
   const Tuning &t = *g.tuning;
@@ -982,6 +1026,7 @@ int launch_tcgen05(int dtype, const GemmArgs &g, void *scratch, size_t scratch_b
     MM_CUDA_TRY(cudaFuncGetAttributes(&attr, prep_b_panels_kernel<false>));
     MM_CUDA_TRY(cudaFuncGetAttributes(&attr, transpose_prep_kernel<float, true>));
     MM_CUDA_TRY(cudaFuncGetAttributes(&attr, transpose_prep_kernel<__half, false>));
+    MM_CUDA_TRY(cudaFuncGetAttributes(&attr, transpose_prep_kernel<unsigned char, false>));
     if (!get_encode_fn()) return fail(MM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     return gemm_dispatch(dtype, nullptr, nullptr, nullptr, g.n, g.k, g.m, g.flags, t, nullptr, nullptr, 0, true, g.stream);
   }

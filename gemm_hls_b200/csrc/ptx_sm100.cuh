@@ -150,7 +150,7 @@ __device__ __forceinline__ void tcgen05_fence_after_sync() {
 }
 
 // ---- tcgen05: MMA ------------------------------------------------------------------------------
-enum : int { KIND_F16 = 0, KIND_TF32 = 1 };
+enum : int { KIND_F16 = 0, KIND_TF32 = 1, KIND_I8 = 2 };
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread for the CTA (pair).
 template <int KIND, int CTA_GROUP>
@@ -166,6 +166,18 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t 
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if (KIND == KIND_I8 && CTA_GROUP == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if (KIND == KIND_I8 && CTA_GROUP == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
   } else if (KIND == KIND_F16 && CTA_GROUP == 1) {
@@ -248,13 +260,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32
   return d;
 }
 
-// Instruction descriptor (upper 32 bits of the 64-bit idesc operand), dense, FP32 accumulate,
-// both operands K-major:
-//   [4,6) D format (1 = F32)   [7,10) A format   [10,13) B format  (0 = F16, 1 = BF16, 2 = TF32)
+// Instruction descriptor (upper 32 bits of the 64-bit idesc operand), dense, A K-major:
+//   [3] saturate (kind::i8 only; 0 = wrap)   [4,6) D format (1 = F32, 2 = S32)
+//   [7,10) A format   [10,13) B format   (kind::f16 / tf32: 0 = F16, 1 = BF16, 2 = TF32;  kind::i8: 0 = unsigned, 1 = signed 8-bit)
 //   [15] A major (0 = K)  [16] B major (0 = K, 1 = MN)   [17,23) N >> 3   [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc(int kind, uint32_t umma_m, uint32_t umma_n,
                                                   bool b_mn_major = false) {
-  return (1u << 4) | ((kind == KIND_TF32 ? 2u : 0u) << 7) | ((kind == KIND_TF32 ? 2u : 0u) << 10) |
+  return ((kind == KIND_I8 ? 2u : 1u) << 4) | ((kind == KIND_TF32 ? 2u : 0u) << 7) | ((kind == KIND_TF32 ? 2u : 0u) << 10) |
          ((b_mn_major ? 1u : 0u) << 16) | ((umma_n >> 3) << 17) | ((umma_m >> 4) << 24);
 }
 

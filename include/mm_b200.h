@@ -77,6 +77,8 @@ enum {
    *     more than 1e-3 at K = 32 and 63 % at K = 544.  The reference's TestSimulation compares half
    *     EXACTLY (test/TestSimulation.cpp:79-85), so the host executables of this project build half
    *     with MM_FLAG_EXACT unless configured with -DMM_HALF_TENSOR=ON.
+   *   - uint8_t (Multiply, Add): tcgen05 kind::i8, exact 32-bit integer accumulation, low byte stored — BIT-IDENTICAL
+   *     to the reference's modulo-256 arithmetic.  Used for K <= 33024 (255^2 * K < 2^31); the CUDA-core kernel beyond.
    *   - float Min / Max (as Map or Reduce): the hardware FMNMX.  Identical to the reference's
    *     `(a < b) ? a : b` for all finite inputs except that a tie between -0 and +0 yields -0 for Min
    *     (+0 for Max) where the reference returns the second operand, and NaN operands are dropped
@@ -164,8 +166,8 @@ MM_API int mm_context_profile_read(mm_context *ctx, double *prep_seconds_sum,
 /* Number of kernels one mm_kernel_enqueue() with these arguments launches (for accounting). */
 MM_API int mm_kernel_launch_count(int dtype, int map_op, int reduce_op, int flags);
 
-/* Name of the compute kernel family mm_kernel_enqueue() would dispatch to
- * ("tcgen05_tf32", "tcgen05_f16", "dmma_f64", "semiring_simt"); static string. */
+/* Name of the compute kernel family mm_kernel_enqueue() would dispatch to for a small problem
+ * ("tcgen05_tf32", "tcgen05_f16", "tcgen05_i8", "dmma_f64", "semiring_simt"); static string. */
 MM_API const char *mm_kernel_path(int dtype, int map_op, int reduce_op, int flags);
 
 /* The reference's simulation entry, extern "C" MatrixMultiplicationKernel(a, b, c, n, k, m)
@@ -202,7 +204,9 @@ enum {
   MM_TUNE_DMMA_TILE_ROWS = 9,      /* 0 = automatic | 64 | 128: CTA tile rows of the double kernel     MM_DMMA_TILE_ROWS */
   MM_TUNE_EXPERIMENT_TF32_NO_ROUND = 10, /* 1: feed raw fp32 bits to kind::tf32 (measures the truncation
                                       bias that motivates the rounding pass; never for production)    MM_EXPERIMENT_TF32_NO_ROUND */
-  MM_TUNE_COUNT = 11
+  MM_TUNE_SEMIRING_RING = 11,      /* 0 | 1: CUDA-core kernel for 4-byte types with both tiles in a TMA ring and no
+                                      block-wide barrier (default 1), or the register-staged kernel       MM_SEMIRING_RING */
+  MM_TUNE_COUNT = 12
 };
 MM_API int mm_context_set_tuning(mm_context *ctx, int knob, int value);
 MM_API int mm_context_get_tuning(mm_context *ctx, int knob, int *value);

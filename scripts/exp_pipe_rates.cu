@@ -21,10 +21,15 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   return r;
 }
 
-enum { FADD, FADD2, FMNMX, FMNMX3, MIX, MIX_SWAP };
+enum { FADD, FADD2, FMNMX, FMNMX3, MIX, MIX_SWAP, MIX_LDS };
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) rate_kernel(float *out, int iters, long long *cycles) {
+  __shared__ __align__(16) float tile[32 * 128];
+  if (MODE == MIX_LDS) {
+    for (int i = threadIdx.x; i < 32 * 128; i += 256) tile[i] = 1e-3f * (i % 97);
+    __syncthreads();
+  }
   float acc[64], a[8], b[8];
   unsigned long long ap[8], bp[8];
 #pragma unroll
@@ -66,7 +71,8 @@ __global__ void __launch_bounds__(256, 2) rate_kernel(float *out, int iters, lon
           asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(x) : "f"(a[(i + 1) % 8]), "f"(b[p]));
           asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(y) : "f"(a[(i + 1) % 8]), "f"(b[p + 4]));
         } else {
-          // 2 FADD2 (k and k+1, columns 2p / 2p+1) -> 2 FMNMX3: four element-steps in four instructions
+          // 2 FADD2 (k and k+1, columns 2p / 2p+1) -> 2 FMNMX3: four element-steps in four instructions.
+          // The A pair is loop-carried (rotated through the chain below), so no add is loop-invariant.
           unsigned long long s0, s1;
           float s0l, s0h, s1l, s1h;
           asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(s0) : "l"(ap[i]), "l"(bp[p]));
@@ -80,6 +86,16 @@ __global__ void __launch_bounds__(256, 2) rate_kernel(float *out, int iters, lon
           asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(x) : "f"(s0l), "f"(s1l));
           asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(y) : "f"(s0h), "f"(s1h));
         }
+      }
+      if (MODE >= MIX) {   // one extra FADD2 per 16 timed instructions: keeps every add of the next iteration new
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(ap[i]) : "l"(bp[i]));
+      }
+    }
+    if (MODE == MIX_LDS) {   // the kernel's fragment traffic: 8 LDS.128 per 128 math instructions
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = *reinterpret_cast<const float4 *>(tile + ((it * 8 + q) % 32) * 128 + (threadIdx.x % 16) * 4 + (q & 1) * 64);
+        bp[q] = pack2(v.x + v.z, v.y + v.w);
       }
     }
   }
@@ -112,8 +128,10 @@ static void run(const char *label, double element_steps_per_instr) {
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaMemcpy(&h_cyc, cyc, sizeof(h_cyc), cudaMemcpyDeviceToHost);
-  // 128 timed instructions per thread and iteration; 16 warps per SM = 4 per scheduler
-  const double instr_per_sched = 4.0 * 128.0 * iters;
+  // 128 timed instructions per thread and iteration; in the mix modes + the 8 chain-advancing packed adds, which
+  // ptxas emits as 16 scalar FADD (SASS: 64 FADD2 + 64 FMNMX3 + 16 FADD per iteration) = 144 issue slots; the LDS
+  // mode's 8 LDS.128 and the 16 adds that consume them are overhead on top, not counted.  16 warps per SM = 4 per scheduler
+  const double instr_per_sched = 4.0 * (MODE >= MIX ? 144.0 : 128.0) * iters;
   const double cyc_per_instr = double(h_cyc) / instr_per_sched;
   const double mhz = double(h_cyc) / (ms * 1e3);
   const double tops_at_1965 = 2.0 * element_steps_per_instr * 32 * 4 * sms * 1965e6 / cyc_per_instr * 1e-12;
@@ -133,5 +151,6 @@ int main() {
   run<FMNMX3>("fmnmx3", 2.0);
   run<MIX>("mix_2fadd2_2fmnmx3", 1.0);
   run<MIX_SWAP>("mix_swapped_second_pair", 1.0);
+  run<MIX_LDS>("mix_plus_8_lds128_per_128", 1.0);
   return 0;
 }

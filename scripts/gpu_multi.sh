@@ -1,28 +1,18 @@
-#!/bin/bash
-# Multi-GPU evidence:  gpurun --gpus N -- 'bash scripts/gpu_multi.sh N [TAG] [quick]'
-# bench.py under torchrun at N GPUs (row-block split, one NCCL broadcast of B) for the float and double
-# configurations, the single-GPU legs measured on the same box, and the native C++ driver (RunHardware with
-# MM_NUM_GPUS: one host thread per GPU, ncclBroadcast of B).  `quick` = the torchrun legs only.
-set +e
-N=${1:-2}; TAG=${2:-r01}; MODE=${3:-full}
-R=${GRAFT_REPO_ROOT:-$(cd "$(dirname "$0")/.." && pwd)}
-cd "$R"
-O=gpurun_out/$TAG
-mkdir -p $O
-nvidia-smi -L | tee $O/multi_gpus_$N.txt
-J='import sys,json; d=json.loads(sys.stdin.read()); c=d["config"]; print("%-12s n_gpus %d ms/step %.3f value %.0f | broadcast of B %s ms | %s" % (sys.argv[1], d["n_gpus"], d["ms_per_step"], d["value"], c.get("broadcast_b_ms"), d["clocks"]["reasons"]))'
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv,noheader
+nvidia-smi topo -m | head -12
+timeout 600 python -m pytest tests/test_variants_gpu.py -q -m gpu -k "multi or default_entry" > gpurun_out/m${NG:-2}_tests.log 2>&1; echo "multi tests rc=$?"; tail -4 gpurun_out/m${NG:-2}_tests.log
+timeout 600 python -m pytest tests/test_zz_host_exec_gpu.py -q -m gpu -k "mm_num_gpus" > gpurun_out/m${NG:-2}_host.log 2>&1; echo "host rc=$?"; tail -3 gpurun_out/m${NG:-2}_host.log
+G=${NG:-2}
 for wl in float16384 double8192; do
-  if [ $MODE != quick ]; then
-    timeout 900 python bench.py --workload $wl --gpus 1 --steps 20 --no-cpu > $O/scale_${wl}_n1.json 2>/dev/null
-    tail -1 $O/scale_${wl}_n1.json | python -c "$J" "$wl"
-  fi
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
-      bench.py --workload $wl --gpus $N --steps 20 --no-cpu > $O/scale_${wl}_n$N.json 2>$O/scale_${wl}_n$N.err
-  tail -1 $O/scale_${wl}_n$N.json | python -c "$J" "$wl" || tail -5 $O/scale_${wl}_n$N.err
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $G --steps 20 --warmup 3 --workload $wl > gpurun_out/m${NG:-2}_bench_${wl}_n$G.log 2>&1; echo "bench $wl rc=$?"
+  tail -1 gpurun_out/m${NG:-2}_bench_${wl}_n$G.log | python -c "
+import sys,json
+try:
+    d=json.loads(sys.stdin.read()); print(d['config']['workload'], 'N=',d['n_gpus'],'value',round(d['value']/1e3,1),'step',round(d['ms_per_step'],3),'kernel',round(d['roofline']['kernel_ms'],3),'prep',round(d['roofline']['prep_ms'],3),'e2e',round(d['e2e']['value']/1e3,1), round(d['e2e']['ms_per_step'],2),'ms', d.get('broadcast_b'))
+except Exception as e: print('parse failed', e)
+"
 done
-if [ $MODE != quick ]; then
-  echo "== native C++ multi-GPU driver"
-  bash scripts/build_host.sh /tmp/hostbuild > /dev/null 2>&1 || echo "host build failed"
-  ( MM_NUM_GPUS=$N /tmp/hostbuild/RunHardware 1024 1024 1024 hw on; echo "rc=$?"
-    MM_NUM_GPUS=$N /tmp/hostbuild/RunHardware 16384 16384 16384 hw off; echo "rc=$?" ) 2>&1 | tee $O/multi_runhardware_$N.log | tail -16
-fi
+bash scripts/build_host.sh /tmp/hb > /dev/null 2>&1
+for g in 1 $G; do MM_NUM_GPUS=$g timeout 300 /tmp/hb/RunHardware 16384 16384 16384 hw off 2>&1 | grep -E "Kernel executed|failed" | tee -a gpurun_out/m${G}_runhardware.log; done
+MM_NUM_GPUS=$G timeout 300 /tmp/hb/RunHardware 2048 2048 2048 hw on 2>&1 | grep -E "Kernel executed|verified|failed|Mismatch" | tee -a gpurun_out/m${G}_runhardware.log

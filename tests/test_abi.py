@@ -42,6 +42,7 @@ def test_library_contains_blackwell_sass(mm):
     sass = r.stdout
     assert "sm_100a" in sass
     assert re.search(r"UTC[A-Z]*MMA", sass), "no tcgen05.mma in SASS"
+    assert "UTCIMMA" in sass, "no integer tcgen05.mma (kind::i8) in SASS"
     assert "LDTM" in sass and "UTMALDG" in sass
     assert "UTMASTG" in sass, "the epilogue's TMA stores are missing"
     assert "DMMA" in sass
@@ -58,6 +59,8 @@ def test_static_queries(mm):
     assert mm.kernel_path(mm.FLOAT, mm.ADD, mm.MIN) == "semiring_simt"
     assert mm.kernel_path(mm.FLOAT, flags=mm.FLAG_EXACT) == "semiring_simt"
     assert mm.kernel_path(mm.INT32) == "semiring_simt"
+    assert mm.kernel_path(mm.UINT8) == "tcgen05_i8" and mm.kernel_path(mm.UINT8, flags=mm.FLAG_EXACT) == "semiring_simt"
+    assert mm.kernel_path(mm.UINT8, mm.ADD, mm.MIN) == "semiring_simt" and mm.launch_count(mm.UINT8) == 1
     # float: B rounding + A rounding + GEMM; half reads both operands in place
     assert mm.launch_count(mm.FLOAT) == 3 and mm.launch_count(mm.DOUBLE) == 1
     assert mm.launch_count(mm.HALF) == 1

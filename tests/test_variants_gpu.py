@@ -110,6 +110,61 @@ def test_dmma_tile_rows(mm, oracle, tile_rows):
             assert max_rel(c, ref) <= TOL["dmma_f64"]
 
 
+@pytest.mark.parametrize("ring", [0, 1])
+@pytest.mark.parametrize("dt,mp,rd", [("FLOAT", "ADD", "MIN"), ("FLOAT", "MULTIPLY", "ADD"), ("FLOAT", "MAX", "MIN"),
+                                      ("INT32", "MULTIPLY", "ADD"), ("UINT32", "ADD", "MAX")])
+def test_semiring_ring_and_staged_kernels_agree(mm, oracle, ring, dt, mp, rd):
+    """4-byte types have two CUDA-core kernels (TMA ring | register-staged, knob semiring_ring): both bit-exact, on
+    ragged shapes (rows past N and columns past M are zero-filled by TMA in the ring kernel, never stored)."""
+    dtype, m_, r_ = getattr(mm, dt), getattr(mm, mp), getattr(mm, rd)
+    flags = mm.FLAG_EXACT if (mp, rd) == ("MULTIPLY", "ADD") else 0
+    with mm.Context(0) as ctx:
+        ctx.set_tuning(semiring_ring=ring)
+        for n, k, m in ((513, 528, 528), (1, 16, 16), (127, 64, 192), (300, 1024, 320)):
+            a, b = oracle.fill(dtype, n, k, m, 31)
+            c, _, _ = ctx.gemm_host(dtype, m_, r_, a, b, n, k, m, flags=flags)
+            ref = oracle.naive(dtype, m_, r_, a, b, n, k, m, threads=8)
+            assert c.tobytes() == ref.tobytes(), (ring, n, k, m)
+
+
+# uint8_t on tcgen05 kind::i8 (SURVEY.md 8 f3): exact integer accumulation, bit-exact modulo 256
+def _u8_inputs(n, k, m, seed, full_range=True):
+    rng = np.random.default_rng(seed)
+    hi = 256 if full_range else 11
+    return rng.integers(0, hi, size=n * k, dtype=np.uint8), rng.integers(0, hi, size=k * m, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("variant", [dict(), dict(cta_group=1), dict(block_n=128), dict(cta_group=1, block_n=128),
+                                     dict(b_mn=0), dict(b_mn=0, block_n=128), dict(tma_store=0), dict(stages=3)], ids=_vid)
+def test_uint8_tensor_path_bit_exact(mm, oracle, variant):
+    assert mm.kernel_path(mm.UINT8) == "tcgen05_i8"
+    with mm.Context(0) as ctx:
+        ctx.set_tuning(**variant)
+        for n, k, m in ((513, 576, 576), (1, 64, 64), (129, 128, 192), (1024, 1024, 1024)):
+            a, b = _u8_inputs(n, k, m, 41)
+            c, _, _ = ctx.gemm_host(mm.UINT8, mm.MULTIPLY, mm.ADD, a, b, n, k, m)
+            ref = oracle.naive(oracle.UINT8, oracle.MULTIPLY, oracle.ADD, a, b, n, k, m, threads=8)
+            assert c.tobytes() == ref.tobytes(), (variant, n, k, m)
+            ct, _, _ = ctx.gemm_host(mm.UINT8, mm.MULTIPLY, mm.ADD, np.ascontiguousarray(a.reshape(n, k).T), b, n, k, m,
+                                     flags=mm.FLAG_TRANSPOSED_A)
+            assert ct.tobytes() == ref.tobytes(), ("transposed A", variant, n, k, m)
+
+
+def test_uint8_accumulator_headroom_and_fallback(mm, oracle):
+    """255^2 * K fits the 32-bit accumulator up to K = 33024 (all-255 inputs: the largest possible sum); longer K takes
+    the CUDA-core kernel.  Both sides of the switch give the reference's bits."""
+    for k in (33024, 33088):
+        n, m = 3, 64
+        a = np.full(n * k, 255, dtype=np.uint8)
+        b = np.full(k * m, 255, dtype=np.uint8)
+        c = mm.matrix_multiplication_kernel(a, b, n, k, m, dtype=mm.UINT8)
+        ref = oracle.naive(oracle.UINT8, oracle.MULTIPLY, oracle.ADD, a, b, n, k, m, threads=8)
+        assert c.tobytes() == ref.tobytes(), k
+        a2, b2 = _u8_inputs(n, k, m, 43)
+        c = mm.matrix_multiplication_kernel(a2, b2, n, k, m, dtype=mm.UINT8)
+        assert c.tobytes() == oracle.naive(oracle.UINT8, oracle.MULTIPLY, oracle.ADD, a2, b2, n, k, m, threads=8).tobytes(), k
+
+
 def test_tuning_rejects_out_of_range_values(mm):
     with mm.Context(0) as ctx:
         for bad in (dict(cta_group=3), dict(block_n=192), dict(stages=9), dict(stages=1), dict(dmma_tile_rows=32),
@@ -285,6 +340,7 @@ MULTI_CASES = [
     ("DOUBLE", "MULTIPLY", "ADD", 300, 264, 136),
     ("FLOAT", "ADD", "MIN", 257, 192, 144),
     ("INT32", "MULTIPLY", "ADD", 130, 64, 96),
+    ("UINT8", "MULTIPLY", "ADD", 513, 576, 576),
 ]
 
 
