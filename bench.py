@@ -128,6 +128,61 @@ class ClockSampler:
                 "reasons": sorted(k for k, v in self.REASONS.items() if bits & v)}
 
 
+def gpu_numa_node(index):
+    """NUMA node the GPU hangs off (PCI sysfs), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]
+        node = int(open(path).read())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def node_cpus(node):
+    cpus = set()
+    try:
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+    except Exception:
+        pass
+    return cpus
+
+
+def alloc_host_rows(torch, rows, cols, np_dtype, blocks):
+    """Page-locked host matrix whose row-blocks `blocks` = [(r0, r1, gpu index), ...] are FIRST-TOUCHED on the NUMA node
+    of the GPU that will copy them (one pinned allocation from one thread puts every page on one socket; the GPUs of the
+    other socket then pull their blocks across the inter-socket link).  numpy's untouched mmap + a toucher thread per
+    block pinned to the node's CPUs + cudaHostRegister.  Returns (numpy array, placement note)."""
+    import numpy as np
+    arr = np.empty((rows, cols), dtype=np_dtype)
+    placed = []
+
+    def touch(r0, r1, cpus):
+        if cpus:
+            try:
+                os.sched_setaffinity(0, cpus)   # pid 0 = the calling THREAD
+            except OSError:
+                pass
+        arr[r0:r1].fill(0)
+
+    for r0, r1, gpu in blocks:
+        node = gpu_numa_node(gpu)
+        cpus = node_cpus(node) if node is not None else set()
+        t = threading.Thread(target=touch, args=(r0, r1, cpus))
+        t.start()
+        t.join()
+        placed.append(node)
+    rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
+    rc = int(rc[0]) if isinstance(rc, tuple) else int(rc)
+    return arr, ("registered page-locked, row-blocks first-touched on NUMA nodes %s" % placed) if rc == 0 else \
+                ("cudaHostRegister failed (%d): pageable" % rc)
+
+
 def host_threads():
     """Host threads for the reference's CPU path: one per PHYSICAL core this process may run on.
 
@@ -460,6 +515,8 @@ def main():
         else:
             peak, peak_note = semiring_peak(dtype_name, mp_name, rd_name, flags)
             roof = {"bound": "cuda_core_issue", "achieved": 1e-12 * local_ops / main_avg_s, "peak": peak, "unit": "TOp/s"}
+            if peak == 74.4:
+                roof["frac_of_measured_mix"] = roof["achieved"] / 52.5
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["kernel"] = path
         roof["kernel_ms"] = 1e3 * main_avg_s
@@ -503,9 +560,14 @@ def main():
         e2e_steps = max(1, min(args.steps, 3))
         e2e_s = 0.0
         if rank == 0:
-            a_host = torch.empty((N, K), dtype=t_dt, pin_memory=True)
-            b_host = torch.empty((K, M), dtype=t_dt, pin_memory=True)
-            c_host = torch.empty((N, M), dtype=t_dt, pin_memory=True)
+            # host matrices: one page-locked array each, its row-blocks placed on the NUMA node of the GPU that copies them
+            # (A and C: the GPUs' row-blocks; B: the K-row slices the GPUs upload)
+            rows_g = (N + world - 1) // world
+            part = max(64, ((K + world - 1) // world + 63) // 64 * 64) if world > 1 else K
+            a_np, place_a = alloc_host_rows(torch, N, K, np_dt, [(min(N, g * rows_g), min(N, (g + 1) * rows_g), g) for g in range(world)])
+            b_np, _ = alloc_host_rows(torch, K, M, np_dt, [(min(K, g * part), min(K, (g + 1) * part), g) for g in range(world)])
+            c_np, _ = alloc_host_rows(torch, N, M, np_dt, [(min(N, g * rows_g), min(N, (g + 1) * rows_g), g) for g in range(world)])
+            a_host, b_host, c_host = torch.from_numpy(a_np), torch.from_numpy(b_np), torch.from_numpy(c_np)
             g2 = torch.Generator(device=dev)
             g2.manual_seed(99)
             for i in range(0, N, 2048):   # the other ranks' row-blocks are synthetic too: draw all of A here
@@ -513,7 +575,6 @@ def main():
                 a_host[i:i + rows_i].copy_(draw((rows_i, K), g2))
             b_host.copy_(b_full)
             torch.cuda.synchronize()
-            a_np, b_np, c_np = a_host.numpy(), b_host.numpy(), c_host.numpy()
             runner = ctx if world == 1 else G.Multi(world)
             if world > 1:
                 runner.set_tuning(**tune)
@@ -523,7 +584,7 @@ def main():
             for _ in range(e2e_steps):
                 runner.gemm_host(dtype, mp, rd, a_np, b_np, N, K, M, flags=flags, out=c_np)
             e2e_s = (time.perf_counter() - t0) / e2e_steps
-            note = ("mm_gemm_host(): pinned host A, B -> device, kernels, C -> pinned host; wall clock" if world == 1 else
+            note = ("mm_gemm_host(): page-locked host A, B -> device, kernels, C -> page-locked host; wall clock" if world == 1 else
                     "mm_multi_gemm_host() from rank 0 over all %d GPUs (peer access: %s): per GPU 1/%d of A and of B over "
                     "PCIe, B gathered over NVLink by the library's kernels, C row-blocks back; wall clock"
                     % (world, runner.peer_access, world))
@@ -533,11 +594,13 @@ def main():
                 e2e_check = check_rows(c_host[idx].to(dev), a_host[idx].to(dev), "e2e")
             out["e2e"] = {"value": 1e-9 * ops_total / e2e_s, "unit": metric,
                           "h2d_bytes_per_step": int(es * (N * K + K * M)), "d2h_bytes_per_step": int(es * N * M),
-                          "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s, "note": note,
+                          "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s, "note": note, "host_memory": place_a,
                           "check": ("3 rows of the host C vs fp64: max rel err %.2e" % e2e_check) if e2e_check is not None else None}
             if world > 1:
                 runner.close()
-            del a_host, c_host
+            for arr in (a_np, b_np, c_np):
+                torch.cuda.cudart().cudaHostUnregister(arr.ctypes.data)
+            del a_host, b_host, c_host
         if world > 1:
             dist.barrier(group=host_group)
 
@@ -558,14 +621,19 @@ def main():
 def semiring_peak(dtype_name, mp_name, rd_name, flags):
     """Derived CUDA-core issue ceiling: one warp instruction per clock and scheduler
     = 148 SMs x 4 x 32 lanes x 1.965 GHz = 37.2e12 lane-instructions/s, 2 ops per element-step.
-      float (Add, Min|Max): 1 FADD2 + 1 FMNMX3 per two element-steps = 1.0 slot per step -> 74.4 TOp/s
-        (the half-rate ALU pipe of the FMNMX3 gives the same bound)
+      float (Add, Min|Max): 1 FADD2 + 1 FMNMX3 per two element-steps = 1.0 slot per step -> 74.4 TOp/s.  MEASURED
+        (scripts/exp_pipe_rates.cu, profiles/r02_exp_semiring.md): each of the two instructions alone issues every
+        cycle, but their mix needs 1.38 cycles per instruction (1.42 with the kernel's fragment loads): the ceiling this
+        instruction mix can reach is 52.5 TOp/s.  `peak` stays the derived 74.4 so that rounds compare; `frac_of_measured_mix`
+        is printed beside it.
       anything else (e.g. float (Multiply, Add) under MM_FLAG_EXACT: 1 FMUL2 per two steps + 1 FADD per step):
         1.5 slots per step -> 49.6"""
     fast_minmax = dtype_name == "float" and mp_name == "Add" and rd_name in ("Min", "Max") and not (flags & 2)
     peak = 74.4 if fast_minmax else 49.6
-    note = ("derived CUDA-core issue ceiling at 1965 MHz, %s (DESIGN.md 3.3); neither HBM- nor tensor-bound"
-            % ("1 FADD2 + 1 FMNMX3 per two element-steps" if fast_minmax else "1.5 issue slots per element-step"))
+    note = ("derived CUDA-core issue ceiling at 1965 MHz, %s (DESIGN.md 3.3); neither HBM- nor tensor-bound%s"
+            % ("1 FADD2 + 1 FMNMX3 per two element-steps" if fast_minmax else "1.5 issue slots per element-step",
+               "; measured ceiling of that instruction mix incl. fragment loads: 52.5 TOp/s (profiles/r02_exp_semiring.md)"
+               if fast_minmax else ""))
     return peak, note
 
 
