@@ -50,11 +50,14 @@ def test_tensor_core_gemm_is_tcgen05_with_tma(mm):
     funcs = {k: v for k, v in _functions("gemm_tcgen05.o").items() if "gemm_tcgen05_kernel" in k}
     assert funcs
     for name, ops in funcs.items():
-        assert _count(ops, "UTCHMMA") > 0, name          # tcgen05.mma
-        assert _count(ops, "UTMALDG") > 0, name          # cp.async.bulk.tensor
+        assert _count(ops, "UTCHMMA") + _count(ops, "UTCIMMA") > 0, name   # tcgen05.mma (kind::tf32/f16 | kind::i8)
+        assert _count(ops, "UTMALDG") > 0, name          # cp.async.bulk.tensor loads
+        assert _count(ops, "UTMASTG") > 0, name          # cp.async.bulk.tensor stores (the epilogue)
         assert _count(ops, "LDTM") > 0, name             # tcgen05.ld (epilogue reads TMEM)
         assert _count(ops, "HMMA") == 0 and _count(ops, "HGMMA") == 0, name   # no legacy tensor path
     assert any(_count(ops, "UTCHMMA.2CTA") > 0 for ops in funcs.values())     # cta_group::2 variant exists
+    assert any(_count(ops, "UTCIMMA.2CTA") > 0 for ops in funcs.values())     # uint8_t on kind::i8, CTA pairs
+    assert len(funcs) == 24                               # {tf32, f16, i8} x {1, 2 CTAs} x {128, 256 columns} x {MN-, K-major B}
 
 
 def test_double_gemm_is_dmma_fed_by_tma_without_ldgsts(mm):
@@ -67,15 +70,15 @@ def test_double_gemm_is_dmma_fed_by_tma_without_ldgsts(mm):
         assert _count(ops, "DFMA") == 0, name             # all FP64 math on the tensor pipe
 
 
-def _semiring(obj, mp, rd):
+def _semiring(obj, mp, rd, kernel="semiring_tile_kernel"):
     """The kernel for (Map, Reduce) in a semiring object; names are Itanium-mangled (3Sum, 7Product, ...)."""
     tag = {"Sum": "3Sum", "Product": "7Product", "Min": "3Min", "Max": "3Max", "And": "3And",
            "MinFast": "7MinFast", "MaxFast": "7MaxFast"}
     out = []
     for name, ops in _functions(obj).items():
-        if "semiring_tile_kernel" not in name:
+        if kernel not in name:
             continue
-        m = re.search(r"semiring_tile_kernelI\w(?:NS_)?(\d[A-Za-z]+)I\w+?E(?:NS_(\d[A-Za-z]+)I\w+?E|(S\d?_))", name)
+        m = re.search(kernel + r"I\w(?:NS_)?(\d[A-Za-z]+)I\w+?E(?:NS_(\d[A-Za-z]+)I\w+?E|(S\d?_))", name)
         assert m, name
         mapped = m.group(1)
         reduced = m.group(2) if m.group(2) else mapped   # a substitution (S2_) repeats the Map type
@@ -90,6 +93,9 @@ def test_packed_float_paths(mm):
     assert _count(addmin, "FADD2") == 512 and _count(addmin, "FMNMX3") == 512     # per 16-k tile: 1 + 1 per two steps
     assert _count(addmin, "FADD") == _count(addmin, "FADD2")                       # no scalar FADD left
     assert _count(addmin, "UTMALDG") > 0                                           # B tile staged by TMA
+    ring = _semiring("semiring_f32_1.o", "Sum", "MinFast", kernel="semiring_ring_kernel")  # the default for 4-byte types
+    assert _count(ring, "FADD2") == 512 and _count(ring, "FMNMX3") == 512 and _count(ring, "FADD") == 512
+    assert _count(ring, "UTMALDG") >= 2 and _count(ring, "LDG") == 0 and _count(ring, "BAR") <= 2   # both tiles by TMA, no barrier in the loop
     exact = _semiring("semiring_f32_0.o", "Product", "Sum")
     assert _count(exact, "FMUL2") == 512 and _count(exact, "FADD") - _count(exact, "FADD2") == 1024
 
@@ -99,7 +105,7 @@ def test_no_fma_contraction_in_any_floating_point_semiring_kernel(mm, suffix):
     seen = 0
     for mp in range(5):
         for name, ops in _functions("semiring_%s_%d.o" % (suffix, mp)).items():
-            if "semiring_tile_kernel" not in name:
+            if "semiring_tile_kernel" not in name and "semiring_ring_kernel" not in name:
                 continue
             seen += 1
             # a contraction multiplies two data registers and adds a third.  What may legitimately appear:
