@@ -788,6 +788,17 @@ int tcgen05_prepare_b(int dtype, const BSource &src, void *bt, unsigned k, unsig
       return MM_OK;
     }
     // float: rounded copy (same layout).  half / unrounded float with slices: plain gather into `bt`.
+    if (!in_place && !parts && ready == nullptr) {
+      // one local array, nobody waiting on panels: the flat elementwise pass (6.3 TB/s against the panel
+      // kernel's 5.1 on a 512 MiB block — the panel order costs row-segment locality)
+      MM_CUDA_TRY(cudaFuncSetAttribute(round_tf32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
+      const size_t count4 = size_t(k) * m / 4;
+      const int blocks = int(std::min<size_t>((count4 + 255) / 256, size_t(num_sms()) * 16));
+      round_tf32_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float4 *>(src.b), static_cast<float4 *>(bt), count4);
+      MM_CUDA_TRY(cudaGetLastError());
+      return MM_OK;
+    }
     const unsigned panel_cols = unsigned(t.block_n());
     const unsigned panels = ceil_div(m, panel_cols);
     const bool publish = ready != nullptr && panels <= B_READY_BYTES / sizeof(unsigned int);

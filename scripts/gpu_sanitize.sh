@@ -1,9 +1,9 @@
 #!/bin/bash
 # compute-sanitizer passes over small ragged invocations of every kernel family + the new tests
 set +e
-mkdir -p gpurun_out/r01
-O=gpurun_out/r01
-echo "== new tests"; timeout 600 python -m pytest tests/test_parity_gpu.py -q -m gpu -k "graph or two_contexts" 2>&1 | tail -5
+TAG=${1:-r02}
+mkdir -p gpurun_out/$TAG
+O=gpurun_out/$TAG
 for tool in memcheck racecheck synccheck; do
   echo "== compute-sanitizer $tool"
   timeout 900 compute-sanitizer --tool $tool --print-limit 5 python scripts/sanitize_small.py > $O/sanitizer_$tool.log 2>&1
