@@ -24,6 +24,7 @@ struct KernelModel {
 KernelModel ModelFor(std::string const &family, mmhost::Shape const &s) {
   if (family == "tcgen05_f16") return {family, 2.0 * 4096, 256, 256, 2};   // UMMA 256x256x16 per 128 clk, CTA pair
   if (family == "tcgen05_tf32") return {family, 2.0 * 2048, 256, 256, 2};  // UMMA 256x256x8  per 128 clk, CTA pair
+  if (family == "tcgen05_i8") return {family, 2.0 * 8192, 256, 256, 2};    // UMMA 256x256x32 per 128 clk, CTA pair
   if (family == "dmma_f64") {
     // DMMA: 64 FMA / clk / SM; 128-row tiles, or 64-row tiles when those fill the last wave better
     // (the launcher's rule, csrc/gemm_dmma.cu: the half-height tile has to win by more than 5 %)

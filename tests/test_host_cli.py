@@ -54,6 +54,15 @@ def test_print_specifications_float(host_float):
     assert _field(slower.stdout, "Ideal performance:") == pytest.approx(148 * 4096 * 1000e-3, rel=1e-4)
 
 
+def test_print_specifications_uint8_uses_the_integer_tensor_model(mm, tmp_path):
+    out = _build(tmp_path, "uint8_t")
+    r = _run(os.path.join(out, "PrintSpecifications"), 16384, 16384, 16384)
+    assert r.returncode == 0, r.stderr
+    assert "uint8_t (Multiply, Add)" in r.stdout and "tcgen05_i8" in r.stdout
+    # kind::i8: 148 SMs x 16384 op/clk x 1965 MHz (twice the 16-bit rate)
+    assert _field(r.stdout, "Ideal performance:") == pytest.approx(148 * 16384 * 1965e-3, rel=1e-4)
+
+
 def test_usage_and_shape_errors_follow_the_reference(host_float):
     r = _run(os.path.join(host_float, "PrintSpecifications"))
     assert r.returncode == 1 and "Usage:" in r.stderr
