@@ -494,10 +494,9 @@ int fan_out(int gpus, Fn fn) {
 }
 
 // Point every device's slice table at the devices' current B buffers (they move when they grow).
-int refresh_parts(mm_multi *mu, int g, size_t b_bytes) {
+int refresh_parts(mm_multi *mu, int g) {
   mm_context *ctx = mu->ctx[g];
   MM_CUDA_TRY(cudaSetDevice(ctx->device));
-  (void)b_bytes;
   std::vector<void *> table(mu->ctx.size());
   for (size_t j = 0; j < mu->ctx.size(); ++j) table[j] = mu->ctx[j]->staging[1].ptr;
   MM_CUDA_TRY(cudaMemcpy(mu->parts_dev[g], table.data(), table.size() * sizeof(void *), cudaMemcpyHostToDevice));
@@ -543,7 +542,7 @@ int multi_gemm_host_locked(mm_multi *mu, int dtype, int map_op, int reduce_op, i
     if (p.rows == 0) p.rows = 1, p.a_host = static_cast<const unsigned char *>(a), p.c_host = nullptr;
     int rc1 = p.upload_b(bp);
     barrier.arrive_and_wait();  // every slice event is recorded and every B buffer has its final address
-    int rc2 = (rc1 == MM_OK && mu->peer) ? refresh_parts(mu, g, size_t(k) * m * es) : MM_OK;
+    int rc2 = (rc1 == MM_OK && mu->peer) ? refresh_parts(mu, g) : MM_OK;
     if (mu->peer) {
       for (int j = 0; j < G; ++j) {
         if (j != g) bp.peer_slices.push_back(mu->ctx[j]->ev_slice);
@@ -834,18 +833,15 @@ int mm_gemm_host(mm_context *ctx, int dtype, int map_op, int reduce_op, int flag
   int rc = check_args(dtype, map_op, reduce_op, a, b, c, n, k, m);
   if (rc != MM_OK) return rc;
   if (!ctx) {
-    std::lock_guard<std::mutex> lock(g_default_mutex);
-    const int gpus = env_int("MM_NUM_GPUS", 1);
-    if (gpus > 1 && !(flags & MM_FLAG_TRANSPOSED_A)) {
-      if (!g_default_multi) {
-        rc = mm_multi_create(gpus, nullptr, &g_default_multi);
-        if (rc != MM_OK) return rc;
-      }
-    } else if (!g_default_ctx) {
-      rc = mm_context_create(env_int("MM_DEVICE", 0), &g_default_ctx);
+    // the per-process default: one context on $MM_DEVICE, or an mm_multi over $MM_NUM_GPUS devices
+    const bool split = env_int("MM_NUM_GPUS", 1) > 1 && !(flags & MM_FLAG_TRANSPOSED_A);
+    {
+      std::lock_guard<std::mutex> lock(g_default_mutex);
+      if (split && !g_default_multi) rc = mm_multi_create(env_int("MM_NUM_GPUS", 1), nullptr, &g_default_multi);
+      if (!split && !g_default_ctx) rc = mm_context_create(env_int("MM_DEVICE", 0), &g_default_ctx);
       if (rc != MM_OK) return rc;
     }
-    if (gpus > 1 && !(flags & MM_FLAG_TRANSPOSED_A)) {
+    if (split) {
       return mm_multi_gemm_host(g_default_multi, dtype, map_op, reduce_op, flags, a, b, c, n, k, m, seconds_device,
                                 seconds_wall);
     }
@@ -976,7 +972,7 @@ int mm_multi_upload(mm_multi *mu, int dtype, int flags, const void *a, const voi
     barrier.arrive_and_wait();
     int rc2 = MM_OK;
     if (rc1 == MM_OK && mu->peer) {
-      rc2 = refresh_parts(mu, g, 0);
+      rc2 = refresh_parts(mu, g);
     }
     barrier.arrive_and_wait();
     if (rc1 == MM_OK && rc2 == MM_OK && mu->peer) {
