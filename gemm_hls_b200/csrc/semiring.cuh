@@ -190,6 +190,26 @@ struct PackedOp<Product<float>> {
   }
 };
 
+// ---- packed pairs (half) -------------------------------------------------------------------------
+// HADD2 / HMUL2 do two IEEE round-to-nearest half operations per instruction, each half rounded exactly like the
+// scalar __hadd_rn / __hmul_rn; the _rn intrinsics are never contracted into an HFMA2 (a single rounding, which
+// Naive<> does not do).  Used when BOTH Map and Reduce are Sum / Product — (Multiply, Add) under MM_FLAG_EXACT, the
+// datapath the half host programs run by default — for two adjacent columns of C at a time.
+template <class Op>
+struct PackedOpH {
+  static constexpr bool value = false;
+};
+template <>
+struct PackedOpH<Sum<__half>> {
+  static constexpr bool value = true;
+  static __device__ __forceinline__ __half2 Apply2(__half2 a, __half2 b) { return __hadd2_rn(a, b); }
+};
+template <>
+struct PackedOpH<Product<__half>> {
+  static constexpr bool value = true;
+  static __device__ __forceinline__ __half2 Apply2(__half2 a, __half2 b) { return __hmul2_rn(a, b); }
+};
+
 // internal operator codes (never cross the C-ABI)
 enum { MM_OP_MIN_FAST = 5, MM_OP_MAX_FAST = 6 };
 

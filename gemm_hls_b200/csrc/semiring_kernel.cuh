@@ -64,11 +64,17 @@ struct SemiringTile {
   static constexpr size_t SMEM_BYTES = A_BYTES + 2 * B_TILE_BYTES + 16 /* two mbarriers */;
 };
 
-// 2 CTAs (16 warps) per SM for 4-byte element types: 64 accumulators + two k-steps of fragments fit
-// in 128 registers without spilling.  8-byte types need the full 255-register budget, and 1- and
-// 2-byte types (one 32-bit register per unpacked element) spill at 128: those run 1 CTA per SM.
+// half with a Sum / Product Map AND Reduce keeps its accumulators as __half2 pairs of adjacent columns (HADD2 / HMUL2).
 template <typename T, class Map, class Reduce>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4) ? 2 : 1)
+struct SemiringHalf2 {
+  static constexpr bool value = std::is_same<T, __half>::value && PackedOpH<Map>::value && PackedOpH<Reduce>::value;
+};
+
+// 2 CTAs (16 warps) per SM for 4-byte element types and packed half: 64 accumulators + two k-steps of fragments fit
+// in 128 registers without spilling.  8-byte types need the full 255-register budget, and unpacked 1- and
+// 2-byte types (one 32-bit register per element) spill at 128: those run 1 CTA per SM.
+template <typename T, class Map, class Reduce>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 || SemiringHalf2<T, Map, Reduce>::value) ? 2 : 1)
 semiring_tile_kernel(const T *__restrict__ A, const __grid_constant__ CUtensorMap tmap_b, T *__restrict__ C,
                      unsigned size_n, unsigned size_k, unsigned size_m,
                      bool TRANSPOSED_A) {
@@ -87,11 +93,17 @@ semiring_tile_kernel(const T *__restrict__ A, const __grid_constant__ CUtensorMa
   const size_t row0 = size_t(blockIdx.y) * BM;
   const size_t col0 = size_t(blockIdx.x) * BN;
 
+  constexpr bool kHalf2 = SemiringHalf2<T, Map, Reduce>::value;
   T acc[8][8];
+  __half2 acc2[8][4];  // kHalf2 only: columns (2p, 2p + 1) of row i
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = Reduce::identity();
+    if constexpr (kHalf2) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc2[i][p] = __half2half2(Reduce::identity());
+    }
   }
 
   Chunk16<T> a_stage[Cfg::CHUNKS_PER_THREAD];
@@ -193,7 +205,24 @@ semiring_tile_kernel(const T *__restrict__ A, const __grid_constant__ CUtensorMa
           bf[u][4 + q] = b1.v[q];
         }
       }
-      if constexpr (std::is_same<T, float>::value && PackedOp<Map>::value) {
+      if constexpr (kHalf2) {
+        // half, Map and Reduce in {Sum, Product}: two adjacent columns per HMUL2 / HADD2 (A element broadcast by
+        // the instruction's half selector), one rounding per Map and per Reduce per element, in Naive<>'s order
+        __half2 bp[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) bp[u][p] = __halves2half2(bf[u][2 * p], bf[u][2 * p + 1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 a0 = __half2half2(af[0][i]), a1 = __half2half2(af[1][i]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const __half2 t0 = PackedOpH<Map>::Apply2(a0, bp[0][p]), t1 = PackedOpH<Map>::Apply2(a1, bp[1][p]);
+            acc2[i][p] = PackedOpH<Reduce>::Apply2(PackedOpH<Reduce>::Apply2(acc2[i][p], t0), t1);
+          }
+        }
+      } else if constexpr (std::is_same<T, float>::value && PackedOp<Map>::value) {
         // float Map = Sum / Product: two adjacent columns per instruction (FADD2 / FMUL2, A element
         // broadcast); a Sum / Product Reduce is packed the same way, Min / Max reduce per element
         // (FMNMX3 over the two k).  Per element the operations and their order are unchanged.
@@ -255,7 +284,13 @@ semiring_tile_kernel(const T *__restrict__ A, const __grid_constant__ CUtensorMa
       if (col + 4 <= size_m) {
         Quad<T> out;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) out.v[q] = acc[i][h * 4 + q];
+        for (int q = 0; q < 4; ++q) {
+          if constexpr (kHalf2) {
+            out.v[q] = (q % 2 == 0) ? __low2half(acc2[i][h * 2 + q / 2]) : __high2half(acc2[i][h * 2 + q / 2]);
+          } else {
+            out.v[q] = acc[i][h * 4 + q];
+          }
+        }
         *reinterpret_cast<Quad<T> *>(C + row * size_m + col) = out;
       }
     }
