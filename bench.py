@@ -5,15 +5,17 @@
 
 One step = one MatrixMultiplicationKernel invocation C = A * B (operand preparation + GEMM, or the
 configured semiring) over one batch of synthetic matrices through the C-ABI of libmm_b200.so.
-For N > 1 (torchrun, one rank per GPU, NCCL) the C row-blocks are split across ranks, B is
-broadcast ONCE from rank 0 before the timed region (no per-step collective), every
-rank multiplies its row-block each step; time = max over ranks, value = total ops / time.
+For N > 1 (torchrun, one rank per GPU, NCCL) C is cut into an r x c grid of blocks, one per rank
+(gemm_hls_b200/multi.py; c = 1 is the plain row-block split), B is broadcast ONCE from rank 0 before the
+timed region (no per-step collective, SURVEY.md 8e), every rank multiplies its block each step;
+time = max over ranks, value = total ops / time.
 
 Printed JSON line (rank 0): see the contract in the task statement; in addition
   roofline      dominant kernel's achieved rate vs the measured peak (MEASURED_PEAKS.json)
   cpu_baseline  the reference's own Naive<> (oracle/_ref, include/Utility.h:18-42) timed on this
                 host's cores on a bounded sample of the same workload (rank 0, N == 1)
-  e2e           the same metric through mm_gemm_host() with HOST (pinned) buffers, H2D + D2H inside
+  e2e           the same metric through ONE host-pointer call for the whole problem, H2D + D2H inside: mm_gemm_host()
+                at N = 1, mm_multi_gemm_host() over all N GPUs (issued by rank 0) at N > 1
 `--impl reference` times only the reference CPU path (oracle/_ref; the oracle port if absent).
 """
 import argparse

@@ -68,7 +68,7 @@ if has cpu; then
 fi
 if has host; then
   echo "== host executables (scripts/build_host.sh, single-GPU programs)"
-  MM_HOST_NO_NCCL=1 bash scripts/build_host.sh /tmp/hostbuild > /dev/null 2>&1 || echo "host build failed"
+  bash scripts/build_host.sh /tmp/hostbuild > /dev/null 2>&1 || echo "host build failed"
   ( /tmp/hostbuild/TestSimulation 513 528 528; echo "TestSimulation rc=$?"
     /tmp/hostbuild/RunHardware 1024 1024 1024 hw on; echo "RunHardware rc=$?"
     MM_POWER_METER=1 /tmp/hostbuild/RunHardware 16384 16384 16384 hw off; echo "RunHardware(power meter) rc=$?"
