@@ -566,11 +566,10 @@ def main():
         if rank == 0:
             # host matrices: one page-locked array each, its row-blocks placed on the NUMA node of the GPU that copies them
             # (A and C: the GPUs' row-blocks; B: the K-row slices the GPUs upload)
-            rows_g = (N + world - 1) // world
-            part = max(64, ((K + world - 1) // world + 63) // 64 * 64) if world > 1 else K
-            a_np, place_a = alloc_host_rows(torch, N, K, np_dt, [(min(N, g * rows_g), min(N, (g + 1) * rows_g), g) for g in range(world)])
-            b_np, _ = alloc_host_rows(torch, K, M, np_dt, [(min(K, g * part), min(K, (g + 1) * part), g) for g in range(world)])
-            c_np, _ = alloc_host_rows(torch, N, M, np_dt, [(min(N, g * rows_g), min(N, (g + 1) * rows_g), g) for g in range(world)])
+            cuts = [G.multi_partition(world, g, N, K) for g in range(world)]      # the library's own partition rule
+            a_np, place_a = alloc_host_rows(torch, N, K, np_dt, [(c[0], c[1], g) for g, c in enumerate(cuts)])
+            b_np, _ = alloc_host_rows(torch, K, M, np_dt, [(c[2], c[3], g) for g, c in enumerate(cuts)])
+            c_np, _ = alloc_host_rows(torch, N, M, np_dt, [(c[0], c[1], g) for g, c in enumerate(cuts)])
             a_host, b_host, c_host = torch.from_numpy(a_np), torch.from_numpy(b_np), torch.from_numpy(c_np)
             g2 = torch.Generator(device=dev)
             g2.manual_seed(99)

@@ -48,7 +48,7 @@ EXPORTS = ["mm_last_error", "mm_version", "mm_dtype_size", "mm_memory_width", "m
            "mm_kernel_path", "mm_gemm_host", "mm_context_set_profiling", "mm_context_profile_read",
            "mm_context_set_tuning", "mm_context_get_tuning", "mm_context_reserve",
            "mm_multi_create", "mm_multi_destroy", "mm_multi_device_count", "mm_multi_context",
-           "mm_multi_peer_access", "mm_multi_gemm_host", "mm_multi_upload", "mm_multi_execute",
+           "mm_multi_peer_access", "mm_multi_partition", "mm_multi_gemm_host", "mm_multi_upload", "mm_multi_execute",
            "mm_multi_download"]
 
 
@@ -97,6 +97,8 @@ def lib():
         L.mm_multi_device_count.argtypes = [vp]
         L.mm_multi_context.argtypes, L.mm_multi_context.restype = [vp, i], vp
         L.mm_multi_peer_access.argtypes = [vp]
+        up = ctypes.POINTER(u)
+        L.mm_multi_partition.argtypes = [i, i, u, u, up, up, up, up]
         L.mm_multi_gemm_host.argtypes = [vp, i, i, i, i, vp, vp, vp, u, u, u, dp, dp]
         L.mm_multi_upload.argtypes = [vp, i, i, vp, vp, u, u, u]
         L.mm_multi_execute.argtypes = [vp, i, i, i, i, u, u, u, dp, dp]
@@ -202,6 +204,13 @@ class Context:
     def gemm_host(self, dtype, map_op, reduce_op, a, b, n, k, m, flags=0, out=None):
         """Host arrays in, host array out (H2D, kernel, D2H); returns (C, seconds_device, seconds_wall)."""
         return _gemm_host(self._h, dtype, map_op, reduce_op, a, b, n, k, m, flags, out)
+
+
+def multi_partition(n_gpus, index, n, k):
+    """(row_begin, row_end, b_row_begin, b_row_end) of GPU `index` in an n_gpus split (mm_multi_partition; no device needed)."""
+    out = [ctypes.c_uint() for _ in range(4)]
+    _check(lib().mm_multi_partition(n_gpus, index, n, k, *[ctypes.byref(o) for o in out]))
+    return tuple(o.value for o in out)
 
 
 class _BorrowedContext(Context):

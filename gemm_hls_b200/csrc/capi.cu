@@ -474,6 +474,30 @@ namespace {
 
 unsigned rows_per_gpu(unsigned n, int g) { return (n + unsigned(g) - 1) / unsigned(g); }
 
+// The partition rule of every mm_multi_* entry (and of mm_multi_partition): rows of A / C, K-row slices of B.
+struct Partition {
+  unsigned r0, r1;   // rows of A and C owned by the GPU
+  unsigned k0, k1;   // K-rows of B it uploads
+  unsigned part_rows, parts;
+};
+Partition partition_for(int gpus, int g, unsigned n, unsigned k, bool sliced_b) {
+  Partition p;
+  const unsigned per = rows_per_gpu(n, gpus);
+  p.r0 = std::min(n, unsigned(g) * per);
+  p.r1 = std::min(n, p.r0 + per);
+  // B row-slices: multiples of 64 k-rows so that a preparation work item never straddles two GPUs
+  p.part_rows = sliced_b ? std::max(64u, (rows_per_gpu(k, gpus) + 63u) / 64u * 64u) : k;
+  p.parts = sliced_b ? (k + p.part_rows - 1) / p.part_rows : 1;
+  if (sliced_b) {
+    p.k0 = std::min(k, unsigned(g) * p.part_rows);
+    p.k1 = (unsigned(g) >= p.parts) ? p.k0 : std::min(k, p.k0 + p.part_rows);   // more GPUs than slices: nothing to upload
+  } else {
+    p.k0 = 0;
+    p.k1 = k;
+  }
+  return p;
+}
+
 // Runs fn(g) on one host thread per device; returns the first error (message re-set on this thread).
 template <class Fn>
 int fan_out(int gpus, Fn fn) {
@@ -510,32 +534,25 @@ int multi_gemm_host_locked(mm_multi *mu, int dtype, int map_op, int reduce_op, i
   }
   const int G = int(mu->ctx.size());
   const size_t es = mm_dtype_size(dtype);
-  const unsigned per = rows_per_gpu(n, G);
-  // B row-slices: multiples of 64 k-rows so that a preparation work item never straddles two GPUs
-  const unsigned part_rows = mu->peer ? std::max(64u, (rows_per_gpu(k, G) + 63u) / 64u * 64u) : k;
-  const unsigned parts = mu->peer ? (k + part_rows - 1) / part_rows : 1;
   std::vector<Pipeline> pipes(G);
   std::vector<BPlan> plans(G);
   std::vector<double> dev_s(G, 0.0);
   HostBarrier barrier(G);
   int rc = fan_out(G, [&](int g) -> int {
-    const unsigned r0 = std::min(n, unsigned(g) * per), r1 = std::min(n, r0 + per);
+    const Partition part = partition_for(G, g, n, k, mu->peer);
+    const unsigned r0 = part.r0, r1 = part.r1;
     Pipeline &p = pipes[g];
     p = Pipeline{mu->ctx[g], dtype, map_op, reduce_op, flags,
                  static_cast<const unsigned char *>(a) + size_t(r0) * k * es, static_cast<const unsigned char *>(b),
                  static_cast<unsigned char *>(c) + size_t(r0) * m * es, r1 - r0, k, m, es,
                  select_path(dtype, map_op, reduce_op, flags, std::max(1u, r1 - r0), k)};
     BPlan &bp = plans[g];
+    bp.k0 = part.k0;
+    bp.k1 = part.k1;
     if (mu->peer) {
-      bp.k0 = std::min(k, unsigned(g) * part_rows);
-      bp.k1 = std::min(k, bp.k0 + part_rows);
-      if (unsigned(g) >= parts) bp.k0 = bp.k1 = k;  // more GPUs than slices
-      bp.parts = parts;
-      bp.part_rows = part_rows;
+      bp.parts = part.parts;
+      bp.part_rows = part.part_rows;
       bp.parts_dev = mu->parts_dev[g];
-    } else {
-      bp.k0 = 0;
-      bp.k1 = k;
     }
     std::lock_guard<std::mutex> lock(mu->ctx[g]->mutex);
     // a GPU without rows still uploads its slice of B: the others read it
@@ -909,6 +926,17 @@ mm_context *mm_multi_context(mm_multi *mu, int index) {
 
 int mm_multi_peer_access(const mm_multi *mu) { return (mu && mu->peer) ? 1 : 0; }
 
+int mm_multi_partition(int n_gpus, int index, unsigned n, unsigned k, unsigned *row_begin, unsigned *row_end,
+                       unsigned *b_row_begin, unsigned *b_row_end) {
+  if (n_gpus < 1 || index < 0 || index >= n_gpus) return fail(MM_ERR_INVALID, "mm_multi_partition: bad device count / index");
+  const Partition p = partition_for(n_gpus, index, n, k, /*sliced_b=*/n_gpus > 1);
+  if (row_begin) *row_begin = p.r0;
+  if (row_end) *row_end = p.r1;
+  if (b_row_begin) *b_row_begin = p.k0;
+  if (b_row_end) *b_row_end = p.k1;
+  return MM_OK;
+}
+
 int mm_multi_gemm_host(mm_multi *mu, int dtype, int map_op, int reduce_op, int flags, const void *a, const void *b,
                        void *c, unsigned n, unsigned k, unsigned m, double *seconds_device, double *seconds_wall) {
   if (!mu) return fail(MM_ERR_INVALID, "null multi-GPU context");
@@ -935,14 +963,12 @@ int mm_multi_upload(mm_multi *mu, int dtype, int flags, const void *a, const voi
   std::lock_guard<std::mutex> lock(mu->mutex);
   const int G = int(mu->ctx.size());
   const size_t es = mm_dtype_size(dtype);
-  const unsigned per = rows_per_gpu(n, G);
-  const unsigned part_rows = mu->peer ? std::max(64u, (rows_per_gpu(k, G) + 63u) / 64u * 64u) : k;
-  const unsigned parts = mu->peer ? (k + part_rows - 1) / part_rows : 1;
   HostBarrier barrier(G);
   rc = fan_out(G, [&](int g) -> int {
     mm_context *ctx = mu->ctx[g];
     std::lock_guard<std::mutex> ctx_lock(ctx->mutex);
-    const unsigned r0 = std::min(n, unsigned(g) * per), r1 = std::min(n, r0 + per);
+    const Partition part = partition_for(G, g, n, k, mu->peer);
+    const unsigned r0 = part.r0, r1 = part.r1, part_rows = part.part_rows, parts = part.parts;
     const unsigned rows = std::max(1u, r1 - r0);
     auto body = [&]() -> int {
       MM_CUDA_TRY(cudaSetDevice(ctx->device));
@@ -951,11 +977,7 @@ int mm_multi_upload(mm_multi *mu, int dtype, int flags, const void *a, const voi
       if ((r = ensure(ctx, ctx->staging[1], size_t(k) * m * es, false)) != MM_OK) return r;
       if ((r = ensure(ctx, ctx->staging[2], size_t(rows) * m * es, false)) != MM_OK) return r;
       unsigned char *db = static_cast<unsigned char *>(ctx->staging[1].ptr);
-      unsigned k0 = 0, k1 = k;
-      if (mu->peer) {
-        k0 = std::min(k, unsigned(g) * part_rows);
-        k1 = (unsigned(g) >= parts) ? k0 : std::min(k, k0 + part_rows);
-      }
+      const unsigned k0 = part.k0, k1 = part.k1;
       const size_t off = size_t(k0) * m * es;
       if (k1 > k0) {
         MM_CUDA_TRY(cudaMemcpyAsync(db + off, static_cast<const unsigned char *>(b) + off, size_t(k1 - k0) * m * es,
@@ -1012,11 +1034,11 @@ int mm_multi_execute(mm_multi *mu, int dtype, int map_op, int reduce_op, int fla
     return fail(MM_ERR_INVALID, "mm_multi_execute: no matching mm_multi_upload (type or sizes differ)");
   }
   const int G = int(mu->ctx.size());
-  const unsigned per = rows_per_gpu(n, G);
   std::vector<double> dev_s(G, 0.0);
   const auto t0 = std::chrono::high_resolution_clock::now();
   int rc = fan_out(G, [&](int g) -> int {
-    const unsigned r0 = std::min(n, unsigned(g) * per), r1 = std::min(n, r0 + per);
+    const Partition part = partition_for(G, g, n, k, mu->peer);
+    const unsigned r0 = part.r0, r1 = part.r1;
     if (r1 == r0) return MM_OK;
     mm_context *ctx = mu->ctx[g];
     return mm_kernel_execute(ctx, dtype, map_op, reduce_op, flags, ctx->staging[0].ptr, ctx->staging[1].ptr,
@@ -1038,9 +1060,9 @@ int mm_multi_download(mm_multi *mu, int dtype, void *c, unsigned n, unsigned m) 
   }
   const int G = int(mu->ctx.size());
   const size_t es = mm_dtype_size(dtype);
-  const unsigned per = rows_per_gpu(n, G);
   return fan_out(G, [&](int g) -> int {
-    const unsigned r0 = std::min(n, unsigned(g) * per), r1 = std::min(n, r0 + per);
+    const Partition part = partition_for(G, g, n, 64, false);
+    const unsigned r0 = part.r0, r1 = part.r1;
     if (r1 == r0) return MM_OK;
     mm_context *ctx = mu->ctx[g];
     return mm_copy_to_host(ctx, static_cast<unsigned char *>(c) + size_t(r0) * m * es, ctx->staging[2].ptr,

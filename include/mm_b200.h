@@ -235,6 +235,13 @@ MM_API int mm_multi_destroy(mm_multi *multi);
 MM_API int mm_multi_device_count(const mm_multi *multi);
 /* The per-device context (for mm_context_set_tuning); owned by `multi`. */
 MM_API mm_context *mm_multi_context(mm_multi *multi, int index);
+/* How an N x K x M problem is cut over `n_gpus` devices — pure arithmetic, no device needed; the same rule every
+ * mm_multi_* entry applies.  GPU `index` owns rows [*row_begin, *row_end) of A and C (ceil(N / G) rows each, tail GPUs
+ * may own fewer or none) and uploads the K-rows [*b_row_begin, *b_row_end) of B (slices of ceil(K / G) rounded up to
+ * a multiple of 64 rows; the whole of B when there is no peer access).  Callers use it to place their host matrices
+ * (e.g. each block on the NUMA node of the GPU that copies it).  Any output pointer may be NULL. */
+MM_API int mm_multi_partition(int n_gpus, int index, unsigned size_n, unsigned size_k, unsigned *row_begin,
+                              unsigned *row_end, unsigned *b_row_begin, unsigned *b_row_end);
 /* 1 if every pair of devices has peer access (NVLink gather), 0 if B falls back to a full upload per GPU. */
 MM_API int mm_multi_peer_access(const mm_multi *multi);
 /* MatrixMultiplicationKernel(a, b, c, n, k, m) with HOST pointers over all G devices; blocking.

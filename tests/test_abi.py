@@ -66,6 +66,28 @@ def test_static_queries(mm):
     assert mm.launch_count(mm.HALF) == 1
 
 
+def test_multi_partition_rule_needs_no_device(mm):
+    """mm_multi_partition: the cut every mm_multi_* entry applies (rows of A / C, K-row slices of B in multiples of 64)."""
+    for n, k, g_count in ((16384, 16384, 8), (513, 528, 3), (3, 64, 4), (8192, 8192, 1), (100, 4096, 7)):
+        rows, slices = [], []
+        for g in range(g_count):
+            r0, r1, k0, k1 = mm.multi_partition(g_count, g, n, k)
+            assert 0 <= r0 <= r1 <= n and 0 <= k0 <= k1 <= k
+            assert (k0 % 64 == 0 and ((k1 - k0) % 64 == 0 or k1 == k)) or g_count == 1
+            rows.append((r0, r1))
+            slices.append((k0, k1))
+        assert rows[0][0] == 0 and slices[0][0] == 0
+        assert sum(b - a for a, b in rows) == n and sum(b - a for a, b in slices) == k
+        for (a0, a1), (b0, b1) in zip(rows, rows[1:]):
+            assert a1 == b0
+        for (a0, a1), (b0, b1) in zip(slices, slices[1:]):
+            assert a1 == b0
+    assert mm.multi_partition(8, 5, 16384, 16384) == (10240, 12288, 10240, 12288)
+    assert mm.multi_partition(4, 3, 3, 64) == (3, 3, 64, 64)          # more GPUs than rows and than slices
+    with pytest.raises(mm.MMError):
+        mm.multi_partition(2, 2, 10, 64)
+
+
 def _has_gpu():
     try:
         import torch
