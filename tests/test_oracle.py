@@ -90,6 +90,40 @@ def test_restatement_equals_reference_naive(oracle, dt, mp, rd, ta, shape):
     assert mine.tobytes() == ref.tobytes()
 
 
+def _special_inputs(np_dtype, n, k, m, seed):
+    """Mixed-sign values with -0, +0, NaN and infinities sprinkled in: what tests/test_variants_gpu.py feeds the GPU."""
+    rng = np.random.default_rng(seed)
+    vals = np.array([-3.5, -1.25, -0.5, 0.75, 1.0, 2.5, 6.0])
+    pool = np.array([-0.0, 0.0, np.nan, np.inf, -np.inf, -0.0, 0.0])
+    out = []
+    for size in (n * k, k * m):
+        x = rng.choice(vals, size=size)
+        idx = rng.choice(size, size=max(4, size // 16), replace=False)
+        x[idx] = rng.choice(pool, size=idx.size)
+        out.append(x.astype(np_dtype))
+    return out
+
+
+@pytest.mark.parametrize("dt,mp,rd,ta,shape", [c for c in REF_CASES if c[0] in ("FLOAT", "DOUBLE", "HALF")])
+def test_restatement_equals_reference_naive_on_special_values(oracle, dt, mp, rd, ta, shape):
+    """The GPU suite checks NaN / signed-zero / infinity behaviour against the restatement; here the restatement itself
+    is pinned to the reference's compiled Naive<> on such inputs (`(a < b) ? a : b`, `a && b`, one rounding per
+    operation — hlslib/xilinx/Operators.h:20-100).  NaN payloads are not compared (C++ leaves them open)."""
+    dtype, m_, r_ = getattr(oracle, dt), getattr(oracle, mp), getattr(oracle, rd)
+    if not oracle.ref_available(dtype, m_, r_, ta):
+        pytest.skip("oracle/_ref not built for this configuration")
+    n, k, m = shape
+    np_dt = {"FLOAT": np.float32, "DOUBLE": np.float64, "HALF": np.float16}[dt]
+    a, b = _special_inputs(np_dt, n, k, m, seed=11)
+    mine = oracle.naive(dtype, m_, r_, a, b, n, k, m, transposed_a=ta)
+    ref = oracle.ref_naive(dtype, m_, r_, a, b, n, k, m, transposed_a=ta)
+    nan_mine, nan_ref = np.isnan(mine.astype(np.float64)), np.isnan(ref.astype(np.float64))
+    assert np.array_equal(nan_mine, nan_ref)
+    ui = {2: np.uint16, 4: np.uint32, 8: np.uint64}[mine.dtype.itemsize]
+    assert np.array_equal(mine.view(ui)[~nan_mine], ref.view(ui)[~nan_ref])      # signs of zeros included
+    assert nan_mine.any() or dt == "HALF" or (mp, rd) != ("MULTIPLY", "ADD")      # the inputs do exercise NaN
+
+
 def test_row_range_and_threads_are_consistent(oracle):
     a, b = oracle.fill(oracle.FLOAT, 40, 32, 48)
     full = oracle.naive(oracle.FLOAT, oracle.ADD, oracle.MIN, a, b, 40, 32, 48)
