@@ -81,3 +81,27 @@ def test_cpu_baseline_object_of_the_b200_arm(oracle):
     assert cb["cores"] == min(threads, rows) and cb["kind"] in ("reference", "port") and cb["unit"] == "GFLOP/s"
     assert cb["value"] == pytest.approx(1e-9 * 2.0 * rows * k * min(m, bench.SAMPLE_COLS) / cb["seconds"], rel=1e-9)
     assert cb["sample"].startswith("%d rows x first %d columns of C" % (rows, min(m, bench.SAMPLE_COLS)))
+
+
+def test_numa_placed_host_matrix_helper_without_a_gpu():
+    """bench.alloc_host_rows, several blocks: an anonymous mapping, each row-block first-touched by its own thread, then
+    registered (here with a stand-in for cudart).  Without NVML / sysfs the placement degrades to 'no affinity'."""
+    import types
+
+    import numpy as np
+    import bench
+    calls = []
+
+    class FakeRuntime:
+        def cudaHostRegister(self, ptr, nbytes, flags):
+            calls.append((ptr, nbytes, flags))
+            return 0
+
+    fake_torch = types.SimpleNamespace(cuda=types.SimpleNamespace(cudart=lambda: FakeRuntime()))
+    arr, keep, note = bench.alloc_host_rows(fake_torch, 1000, 64, np.float32, [(0, 500, 0), (500, 1000, 1)])
+    assert arr.shape == (1000, 64) and arr.dtype == np.float32 and arr.flags["C_CONTIGUOUS"] and arr.flags["WRITEABLE"]
+    assert calls == [(arr.ctypes.data, 1000 * 64 * 4, 0)] and keep is not None
+    assert note.startswith("registered page-locked") and not arr.any()
+    arr[:] = 3.0
+    assert float(arr.sum()) == 3.0 * 64000
+    assert bench.node_cpus(10 ** 6) == set()       # a node that does not exist
