@@ -62,12 +62,16 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tile_sweep.csv"))
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--small", action="store_true", help="nine configurations around the default (one knob at a time)")
     ap.add_argument("--no-ncu", action="store_true", help="skip the DRAM-traffic capture (faster)")
     args = ap.parse_args()
     size, eb = SHAPES.get(args.workload, (16384, 4))
     base = dict(cta_group=2, block_n=256, stages=0, raster_rows=2048, tma_store=1, b_mn=1)
     if args.quick:
         grid = [dict(base), dict(base, cta_group=1)]
+    elif args.small:
+        grid = [dict(base), dict(base, cta_group=1), dict(base, block_n=128), dict(base, stages=3), dict(base, stages=4),
+                dict(base, raster_rows=1024), dict(base, raster_rows=4096), dict(base, tma_store=0), dict(base, b_mn=0)]
     else:
         grid = []
         for cg, bn in ((2, 256), (1, 256), (2, 128), (1, 128)):
