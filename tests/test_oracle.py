@@ -10,8 +10,13 @@ import os
 import numpy as np
 import pytest
 
+import sys
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+GOLDEN_SPECIAL = json.load(open(os.path.join(HERE, "golden", "golden_special.json")))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import special_inputs  # noqa: E402
 
 
 def _id(rec):
@@ -30,6 +35,20 @@ def test_oracle_matches_golden(oracle, rec):
     assert hashlib.sha256(c.tobytes()).hexdigest() == rec["c_sha256"]
     assert repr(float(c.astype(np.float64).flat[0])) == rec["c_first"]
     assert repr(float(c.astype(np.float64).sum())) == rec["c_sum"]
+
+
+@pytest.mark.parametrize("rec", GOLDEN_SPECIAL, ids=lambda r: "%s-%s-%dx%dx%d" % (r["config"], r["inputs"], r["n"], r["k"], r["m"]))
+def test_oracle_matches_golden_on_non_recipe_inputs(oracle, rec):
+    """The restatement reproduces the reference-generated records on full-range bytes, mixed signs and NaN / signed-zero /
+    infinity inputs (tests/golden/golden_special.json) — here and on the GPU box, where /root/reference does not exist."""
+    dtype, n, k, m = rec["dtype"], rec["n"], rec["k"], rec["m"]
+    a, b = special_inputs.make(rec["inputs"], oracle.NP_DTYPE[dtype], n, k, m, rec["seed"])
+    assert hashlib.sha256(a.tobytes()).hexdigest() == rec["a_sha256"]      # the generator is the one the records were made with
+    assert hashlib.sha256(b.tobytes()).hexdigest() == rec["b_sha256"]
+    c = oracle.naive(dtype, rec["map"], rec["reduce"], a, b, n, k, m, threads=4)
+    assert special_inputs.canonical_sha256(c) == rec["c_sha256_nan_canonical"]
+    if np.issubdtype(c.dtype, np.floating):
+        assert int(np.isnan(c.astype(np.float64)).sum()) == rec["c_nan_count"]
 
 
 def test_oracle_matches_golden_1024_sampled_rows(oracle):

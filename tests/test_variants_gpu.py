@@ -12,12 +12,18 @@
      the same code that runs over NVLink;
   5. argument checks that need a device (alignment, tuning ranges, scratch growth under capture).
 """
+import json
 import os
+import sys
 
 import numpy as np
 import pytest
 
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import special_inputs  # noqa: E402
+
 pytestmark = pytest.mark.gpu
+GOLDEN_SPECIAL = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_special.json")))
 
 TOL = {"tcgen05_tf32": 5e-4, "dmma_f64": 1e-12, "tcgen05_f16": 1e-3}
 
@@ -128,10 +134,8 @@ def test_semiring_ring_and_staged_kernels_agree(mm, oracle, ring, dt, mp, rd):
 
 
 # uint8_t on tcgen05 kind::i8: exact integer accumulation, bit-exact modulo 256
-def _u8_inputs(n, k, m, seed, full_range=True):
-    rng = np.random.default_rng(seed)
-    hi = 256 if full_range else 11
-    return rng.integers(0, hi, size=n * k, dtype=np.uint8), rng.integers(0, hi, size=k * m, dtype=np.uint8)
+def _u8_inputs(n, k, m, seed):
+    return special_inputs.full_range_bytes(n, k, m, seed)
 
 
 @pytest.mark.parametrize("variant", [dict(), dict(cta_group=1), dict(block_n=128), dict(cta_group=1, block_n=128),
@@ -193,21 +197,8 @@ FLOATING = ("FLOAT", "DOUBLE", "HALF")
 
 
 def signed_inputs(mm, dtype, n, k, m, seed, special=False):
-    """Mixed-sign data without zeros; `special` sprinkles -0, +0, NaN and infinities (floating types)."""
-    rng = np.random.default_rng(seed)
-    npdt = mm.NP_DTYPE[dtype]
-    if np.issubdtype(npdt, np.floating):
-        vals = np.array([-3.5, -1.25, -0.5, 0.75, 1.0, 2.5, 6.0], dtype=np.float64)
-        a = rng.choice(vals, size=n * k)
-        b = rng.choice(vals, size=k * m)
-        if special:
-            pool = np.array([-0.0, 0.0, np.nan, np.inf, -np.inf, -0.0, 0.0])
-            for arr in (a, b):
-                idx = rng.choice(arr.size, size=max(4, arr.size // 16), replace=False)
-                arr[idx] = rng.choice(pool, size=idx.size)
-        return a.astype(npdt), b.astype(npdt)
-    lo = -4 if np.issubdtype(npdt, np.signedinteger) else 0
-    return (rng.integers(lo, 5, size=n * k).astype(npdt), rng.integers(lo, 5, size=k * m).astype(npdt))
+    """Mixed-sign data without zeros; `special` sprinkles -0, +0, NaN and infinities (tests/golden/special_inputs.py)."""
+    return special_inputs.signed(mm.NP_DTYPE[dtype], n, k, m, seed, special)
 
 
 def _all_semirings():
@@ -245,6 +236,24 @@ def test_semiring_default_flags_shapes(mm, oracle, dt, mp, rd, n, k, m):
     c = mm.matrix_multiplication_kernel(a, b, n, k, m, dtype=dtype, map_op=m_, reduce_op=r_, flags=0)
     ref = oracle.naive(dtype, m_, r_, a, b, n, k, m, threads=8)
     assert c.tobytes() == ref.tobytes()
+
+
+@pytest.mark.parametrize("rec", GOLDEN_SPECIAL, ids=lambda r: "%s-%s-%dx%dx%d" % (r["config"], r["inputs"], r["n"], r["k"], r["m"]))
+def test_golden_records_on_non_recipe_inputs(mm, rec):
+    """Records produced by the reference's OWN Naive<> (tests/golden/make_golden_special.py) on inputs its recipe never
+    draws: full-range bytes (uint8_t on tcgen05 kind::i8), mixed signs (default flags, FMNMX), NaN / signed zeros /
+    infinities (MM_FLAG_EXACT).  Compared by SHA-256 with NaNs canonicalised — no oracle in between."""
+    import hashlib
+    dtype, n, k, m = rec["dtype"], rec["n"], rec["k"], rec["m"]
+    a, b = special_inputs.make(rec["inputs"], mm.NP_DTYPE[dtype], n, k, m, rec["seed"])
+    assert hashlib.sha256(a.tobytes()).hexdigest() == rec["a_sha256"] and hashlib.sha256(b.tobytes()).hexdigest() == rec["b_sha256"]
+    flags = mm.FLAG_EXACT if rec["inputs"] == "special" else 0
+    c = mm.matrix_multiplication_kernel(a, b, n, k, m, dtype=dtype, map_op=rec["map"], reduce_op=rec["reduce"], flags=flags)
+    assert special_inputs.canonical_sha256(c) == rec["c_sha256_nan_canonical"]
+    if rec["inputs"] != "special":   # the exact datapath reproduces the non-special records too
+        ce = mm.matrix_multiplication_kernel(a, b, n, k, m, dtype=dtype, map_op=rec["map"], reduce_op=rec["reduce"],
+                                             flags=mm.FLAG_EXACT)
+        assert special_inputs.canonical_sha256(ce) == rec["c_sha256_nan_canonical"]
 
 
 def _bits_equal_nan_aware(c, ref):
